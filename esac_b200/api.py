@@ -1,0 +1,392 @@
+"""Host-side mirror of the reference's `esac` extension module on top of libesac_b200.so.
+
+`forward` / `backward` keep the positional signatures of esac_forward / esac_backward
+(/root/reference/code/esac/esac.cpp:64-77, 213-230; bound at esac.cpp:513-516) so
+train_esac.py:151-168 and test_esac.py:192-205 run unchanged with `import esac` resolving to the
+top-level `esac.py` shim of this repository.  Tensors may be CPU tensors (what the reference's
+callers pass) or CUDA tensors (no host round trip), or numpy arrays.
+
+There is no CPU implementation behind this module: if libesac_b200.so is missing or no CUDA device is
+visible, calls raise RuntimeError.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from pathlib import Path
+
+import numpy as np
+
+_HERE = Path(__file__).resolve().parent
+LIB_PATH = _HERE / "libesac_b200.so"
+
+
+class Stats(C.Structure):
+    _fields_ = [("M", C.c_int), ("winner", C.c_int), ("n_contrib", C.c_int), ("refine_rounds", C.c_int),
+                ("entropy", C.c_double), ("expected_loss", C.c_double),
+                ("ms_h2d", C.c_float), ("ms_prep", C.c_float), ("ms_sample", C.c_float), ("ms_score", C.c_float),
+                ("ms_select", C.c_float), ("ms_refine", C.c_float), ("ms_backward", C.c_float), ("ms_total", C.c_float),
+                ("score_launches", C.c_int), ("kernel_launches", C.c_int),
+                ("score_ppt", C.c_int), ("score_grid", C.c_int), ("refine_group", C.c_int)]
+
+    def as_dict(self):
+        return {k: getattr(self, k) for k, _ in self._fields_}
+
+
+_lib = None
+
+
+def load_library() -> C.CDLL:
+    """dlopen libesac_b200.so and declare the prototypes of include/esac_b200.h."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not LIB_PATH.exists():
+        raise RuntimeError(f"{LIB_PATH} is not built: run `python -m esac_b200.build` "
+                           "(or __graft_entry__.build()); there is no CPU fallback")
+    lib = C.CDLL(str(LIB_PATH))
+    vp, i32, i64, f32, f64 = C.c_void_p, C.c_int, C.c_int64, C.c_float, C.c_double
+    lib.esacb200_create.argtypes = [i32, C.POINTER(vp)]
+    lib.esacb200_create.restype = i32
+    lib.esacb200_destroy.argtypes = [vp]
+    lib.esacb200_destroy.restype = None
+    lib.esacb200_last_error.argtypes = [vp]
+    lib.esacb200_last_error.restype = C.c_char_p
+    lib.esacb200_set_stream.argtypes = [vp, vp]
+    lib.esacb200_set_seed.argtypes = [vp, C.c_uint64]
+    lib.esacb200_set_option.argtypes = [vp, C.c_char_p, f64]
+    lib.esacb200_inject_cells.argtypes = [vp, vp, i32, i32]
+    cam = [i32, i32, f32, f32, f32, f32, f32, f32, f32, i32]  # shiftX .. subSampling
+    lib.esacb200_forward.argtypes = [vp, vp, i32, i32, i32, vp, i64, i32, vp] + cam + [C.POINTER(i32)]
+    lib.esacb200_backward.argtypes = [vp, vp, vp, i32, i32, i32, vp, i64, i32, vp, f32, f32, f32] + cam + [C.POINTER(f64)]
+    lib.esacb200_score_poses.argtypes = [vp, vp, i32, i32, i32, vp, i64, i32, vp] + cam + [vp]
+    lib.esacb200_refine_poses.argtypes = [vp, vp, i32, i32, i32, vp, i64, i32, vp, i32, i32, f32, f32, f32, f32, f32, i32, vp, vp]
+    lib.esacb200_get_stats.argtypes = [vp, C.POINTER(Stats)]
+    lib.esacb200_get_hypotheses.argtypes = [vp, vp, vp, vp, vp, vp, vp, vp]
+    lib.esacb200_device_info.argtypes = [vp, C.POINTER(i32), C.c_char_p, i32]
+    for name in ("set_stream", "set_seed", "set_option", "inject_cells", "forward", "backward", "score_poses",
+                 "refine_poses", "get_stats", "get_hypotheses", "device_info"):
+        getattr(lib, "esacb200_" + name).restype = i32
+    # host test hooks (include/esac_b200_testhooks.h)
+    lib.esacb200_host_rodrigues.argtypes = [vp, vp, vp]
+    lib.esacb200_host_rodrigues.restype = None
+    lib.esacb200_host_rodrigues_inv.argtypes = [vp, vp]
+    lib.esacb200_host_rodrigues_inv.restype = None
+    lib.esacb200_host_p3p_all.argtypes = [vp, vp, vp, vp]
+    lib.esacb200_host_p3p_all.restype = i32
+    lib.esacb200_host_p3p_pose.argtypes = [vp, vp, f32, f32, f32, f32, vp, C.POINTER(i32)]
+    lib.esacb200_host_p3p_pose.restype = i32
+    lib.esacb200_host_project.argtypes = [vp, f32, f32, f32, vp, vp, vp, vp]
+    lib.esacb200_host_project.restype = None
+    lib.esacb200_host_loss.argtypes = [vp, vp, f64, f64, f64]
+    lib.esacb200_host_loss.restype = f64
+    lib.esacb200_host_dloss.argtypes = [vp, vp, f64, f64, f64, vp]
+    lib.esacb200_host_dloss.restype = None
+    lib.esacb200_host_pose2trans.argtypes = [vp, vp]
+    lib.esacb200_host_pose2trans.restype = None
+    lib.esacb200_host_trans2pose.argtypes = [vp, vp]
+    lib.esacb200_host_trans2pose.restype = None
+    lib.esacb200_host_dprojectdobj.argtypes = [vp, vp, vp, f32, f32, f32, f32, vp]
+    lib.esacb200_host_dprojectdobj.restype = None
+    lib.esacb200_host_pinv6.argtypes = [vp, vp]
+    lib.esacb200_host_pinv6.restype = None
+    lib.esacb200_host_draw_cells.argtypes = [C.c_uint64, C.c_uint32, C.c_uint32, i32, i32, vp]
+    lib.esacb200_host_draw_cells.restype = None
+    _lib = lib
+    return lib
+
+
+# ------------------------------------------------------------------------------------------------
+# contexts (one per device) -- the analogue of the reference's static ThreadRand state
+# ------------------------------------------------------------------------------------------------
+class Context:
+    def __init__(self, device: int = 0):
+        self.lib = load_library()
+        h = C.c_void_p()
+        rc = self.lib.esacb200_create(int(device), C.byref(h))
+        if rc != 0:
+            raise RuntimeError(f"esac_b200: cannot create a context on CUDA device {device} (status {rc}); "
+                               "this implementation has no CPU path")
+        self.handle = h
+        self.device = int(device)
+
+    def close(self):
+        if getattr(self, "handle", None):
+            self.lib.esacb200_destroy(self.handle)
+            self.handle = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def check(self, rc: int):
+        if rc != 0:
+            msg = self.lib.esacb200_last_error(self.handle)
+            raise RuntimeError(f"esac_b200 (status {rc}): {msg.decode() if msg else ''}")
+
+    # additive API ------------------------------------------------------------------------------
+    def set_seed(self, seed: int):
+        self.check(self.lib.esacb200_set_seed(self.handle, C.c_uint64(seed & ((1 << 64) - 1))))
+
+    def set_option(self, key: str, value: float):
+        self.check(self.lib.esacb200_set_option(self.handle, key.encode(), float(value)))
+
+    def set_stream(self, stream_ptr: int):
+        self.check(self.lib.esacb200_set_stream(self.handle, C.c_void_p(stream_ptr or None)))
+
+    def inject_cells(self, cells):
+        if cells is None:
+            self.check(self.lib.esacb200_inject_cells(self.handle, None, 0, 0))
+            return
+        cells = np.ascontiguousarray(cells, np.int32)
+        assert cells.ndim == 4 and cells.shape[2:] == (4, 2), "cells must be [M, T, 4, 2] (x, y)"
+        self.check(self.lib.esacb200_inject_cells(self.handle, cells.ctypes.data, cells.shape[0], cells.shape[1]))
+
+    def stats(self) -> dict:
+        s = Stats()
+        self.check(self.lib.esacb200_get_stats(self.handle, C.byref(s)))
+        return s.as_dict()
+
+    def device_info(self) -> dict:
+        n = C.c_int()
+        buf = C.create_string_buffer(128)
+        self.check(self.lib.esacb200_device_info(self.handle, C.byref(n), buf, 128))
+        return {"sm_count": n.value, "name": buf.value.decode()}
+
+    def hypotheses(self, losses: bool = False) -> dict:
+        M = self.stats()["M"]
+        out = {"poses": np.zeros((M, 6)), "cells": np.zeros((M, 4, 2), np.int32), "tries": np.zeros(M, np.int32),
+               "scores": np.zeros(M), "probs": np.zeros(M), "refined": np.zeros((M, 6))}
+        lo = np.zeros(M) if losses else None
+        self.check(self.lib.esacb200_get_hypotheses(self.handle, out["poses"].ctypes.data, out["cells"].ctypes.data,
+                                                    out["tries"].ctypes.data, out["scores"].ctypes.data,
+                                                    out["probs"].ctypes.data, out["refined"].ctypes.data,
+                                                    lo.ctypes.data if losses else None))
+        if losses:
+            out["losses"] = lo
+        return out
+
+
+_contexts: dict[int, Context] = {}
+
+
+def context(device: int | None = None) -> Context:
+    if device is None:
+        device = 0
+        try:
+            import torch
+            if torch.cuda.is_available():
+                device = torch.cuda.current_device()
+        except Exception:
+            pass
+    if device not in _contexts:
+        _contexts[device] = Context(device)
+    return _contexts[device]
+
+
+# ------------------------------------------------------------------------------------------------
+# tensor plumbing
+# ------------------------------------------------------------------------------------------------
+_TORCH_NAMES = {"torch.float32": "Float", "torch.float64": "Double", "torch.float16": "Half", "torch.int64": "Long",
+                "torch.int32": "Int", "torch.bfloat16": "BFloat16", "torch.uint8": "Byte", "torch.int16": "Short",
+                "torch.int8": "Char", "torch.bool": "Bool"}
+_NP_NAMES = {"float32": "Float", "float64": "Double", "float16": "Half", "int64": "Long", "int32": "Int"}
+
+
+def _is_torch(t) -> bool:
+    return type(t).__module__.startswith("torch")
+
+
+def _dtype_name(t) -> str:
+    if _is_torch(t):
+        return _TORCH_NAMES.get(str(t.dtype), str(t.dtype))
+    return _NP_NAMES.get(str(np.asarray(t).dtype), str(np.asarray(t).dtype))
+
+
+def _check(t, want: str, rank: int, what: str):
+    """Same failure mode as at::Tensor::accessor<T, N>() in the reference (esac.cpp:80-84): RuntimeError."""
+    have = _dtype_name(t)
+    if have != want:
+        raise RuntimeError(f"expected scalar type {want} but found {have} ({what})")
+    nd = t.dim() if _is_torch(t) else np.asarray(t).ndim
+    if nd != rank:
+        raise RuntimeError(f"expected {rank} dims but tensor has {nd} ({what})")
+
+
+class _Arg:
+    """Pointer view of a tensor argument; keeps temporaries alive and writes results back."""
+
+    def __init__(self, t, writable=False, need_contig=True):
+        self.orig = t
+        self.writable = writable
+        self.tmp = None
+        if _is_torch(t):
+            self.is_cuda = t.is_cuda
+            self.device = t.device.index if t.is_cuda else None
+            v = t
+            if need_contig and not t.is_contiguous():
+                v = t.contiguous()
+                self.tmp = v
+            self.view = v
+            self.ptr = v.data_ptr()
+        else:
+            a = np.asarray(t)
+            self.is_cuda = False
+            self.device = None
+            v = a
+            if need_contig and not a.flags["C_CONTIGUOUS"]:
+                v = np.ascontiguousarray(a)
+                self.tmp = v
+            self.view = v
+            self.ptr = v.ctypes.data
+
+    def finish(self):
+        if self.writable and self.tmp is not None:
+            if _is_torch(self.orig):
+                self.orig.copy_(self.tmp)
+            else:
+                np.copyto(np.asarray(self.orig), self.tmp)
+
+
+def _assign_arg(t):
+    """hypAssignment: int64 [M], any stride (stride 0 for expert.expand(), test_esac.py:173)."""
+    if _is_torch(t):
+        M = int(t.shape[0])
+        stride = int(t.stride(0)) if M > 0 else 1
+        return t.data_ptr(), stride, M, (t.device.index if t.is_cuda else None), t
+    a = np.asarray(t)
+    M = int(a.shape[0])
+    stride = int(a.strides[0] // a.itemsize) if M > 0 else 1
+    return a.ctypes.data, stride, M, None, a
+
+
+def _pick_ctx(*devices) -> Context:
+    devs = {d for d in devices if d is not None}
+    if len(devs) > 1:
+        raise RuntimeError(f"esac_b200: tensors live on different CUDA devices {sorted(devs)}")
+    ctx = context(next(iter(devs)) if devs else None)
+    stream = 0
+    if devs:
+        import torch
+        stream = torch.cuda.current_stream(ctx.device).cuda_stream
+    ctx.set_stream(stream)
+    return ctx
+
+
+# ------------------------------------------------------------------------------------------------
+# the reference's two entry points
+# ------------------------------------------------------------------------------------------------
+def forward(sceneCoordinates, hypAssignment, outPose, shiftX, shiftY, focalLength, ppointX, ppointY,
+            inlierThreshold, inlierAlpha, inlierBeta, maxReproj, subSampling) -> int:
+    """esac.forward (esac.cpp:64-190): writes the estimated camera pose into outPose (4x4, in place) and
+    returns the index of the winning expert."""
+    _check(sceneCoordinates, "Float", 4, "sceneCoordinates")
+    _check(hypAssignment, "Long", 1, "hypAssignment")
+    _check(outPose, "Float", 2, "outPose")
+    if tuple(sceneCoordinates.shape)[1] != 3:
+        raise RuntimeError("sceneCoordinates must be [E, 3, H, W]")
+    if tuple(outPose.shape) != (4, 4):
+        raise RuntimeError("outPose must be [4, 4]")
+    co = _Arg(sceneCoordinates)
+    op = _Arg(outPose, writable=True)
+    aptr, astride, M, adev, _keep = _assign_arg(hypAssignment)
+    ctx = _pick_ctx(co.device, op.device, adev)
+    E, _, H, W = (int(s) for s in sceneCoordinates.shape)
+    expert = C.c_int(-1)
+    ctx.check(ctx.lib.esacb200_forward(ctx.handle, co.ptr, E, H, W, aptr, astride, M, op.ptr, int(shiftX), int(shiftY),
+                                       float(focalLength), float(ppointX), float(ppointY), float(inlierThreshold),
+                                       float(inlierAlpha), float(inlierBeta), float(maxReproj), int(subSampling),
+                                       C.byref(expert)))
+    op.finish()
+    return int(expert.value)
+
+
+def backward(sceneCoordinates, outGradients, hypAssignment, gtPose, wLossRot, wLossTrans, lossCut, shiftX, shiftY,
+             focalLength, ppointX, ppointY, inlierThreshold, inlierAlpha, inlierBeta, maxReproj, subSampling) -> float:
+    """esac.backward (esac.cpp:213-511): accumulates d(expected pose loss)/d(sceneCoordinates) into
+    outGradients (in place, +=) and returns the expected loss."""
+    _check(sceneCoordinates, "Float", 4, "sceneCoordinates")
+    _check(outGradients, "Float", 4, "outGradients")
+    _check(hypAssignment, "Long", 1, "hypAssignment")
+    _check(gtPose, "Float", 2, "gtPose")
+    if tuple(sceneCoordinates.shape)[1] != 3 or tuple(outGradients.shape) != tuple(sceneCoordinates.shape):
+        raise RuntimeError("sceneCoordinates / outGradients must both be [E, 3, H, W]")
+    if tuple(gtPose.shape) != (4, 4):
+        raise RuntimeError("gtPose must be [4, 4]")
+    co = _Arg(sceneCoordinates)
+    gr = _Arg(outGradients, writable=True)
+    gt = _Arg(gtPose)
+    aptr, astride, M, adev, _keep = _assign_arg(hypAssignment)
+    ctx = _pick_ctx(co.device, gr.device, gt.device, adev)
+    E, _, H, W = (int(s) for s in sceneCoordinates.shape)
+    loss = C.c_double(0.0)
+    ctx.check(ctx.lib.esacb200_backward(ctx.handle, co.ptr, gr.ptr, E, H, W, aptr, astride, M, gt.ptr, float(wLossRot),
+                                        float(wLossTrans), float(lossCut), int(shiftX), int(shiftY), float(focalLength),
+                                        float(ppointX), float(ppointY), float(inlierThreshold), float(inlierAlpha),
+                                        float(inlierBeta), float(maxReproj), int(subSampling), C.byref(loss)))
+    gr.finish()
+    return float(loss.value)
+
+
+# ------------------------------------------------------------------------------------------------
+# additive entry points
+# ------------------------------------------------------------------------------------------------
+def score_poses(sceneCoordinates, hypAssignment, poses6, shiftX, shiftY, focalLength, ppointX, ppointY,
+                inlierThreshold, inlierAlpha, inlierBeta, maxReproj, subSampling) -> np.ndarray:
+    """Soft-inlier scores (getReproErrs + getHypScores) of given scene poses [M, 6] = (rvec, tvec)."""
+    _check(sceneCoordinates, "Float", 4, "sceneCoordinates")
+    _check(hypAssignment, "Long", 1, "hypAssignment")
+    co = _Arg(sceneCoordinates)
+    aptr, astride, M, adev, _keep = _assign_arg(hypAssignment)
+    poses6 = np.ascontiguousarray(poses6, np.float64)
+    assert poses6.shape == (M, 6)
+    ctx = _pick_ctx(co.device, adev)
+    E, _, H, W = (int(s) for s in sceneCoordinates.shape)
+    out = np.zeros(M)
+    ctx.check(ctx.lib.esacb200_score_poses(ctx.handle, co.ptr, E, H, W, aptr, astride, M, poses6.ctypes.data, int(shiftX),
+                                           int(shiftY), float(focalLength), float(ppointX), float(ppointY),
+                                           float(inlierThreshold), float(inlierAlpha), float(inlierBeta), float(maxReproj),
+                                           int(subSampling), out.ctypes.data))
+    return out
+
+
+def refine_poses(sceneCoordinates, hypAssignment, poses6, shiftX, shiftY, focalLength, ppointX, ppointY,
+                 inlierThreshold, maxReproj, subSampling):
+    """refineHyp for every given pose.  Returns (refined [M, 6], accepted rounds [M], final inlier counts [M])."""
+    _check(sceneCoordinates, "Float", 4, "sceneCoordinates")
+    _check(hypAssignment, "Long", 1, "hypAssignment")
+    co = _Arg(sceneCoordinates)
+    aptr, astride, M, adev, _keep = _assign_arg(hypAssignment)
+    poses6 = np.array(poses6, np.float64, order="C", copy=True)
+    assert poses6.shape == (M, 6)
+    ctx = _pick_ctx(co.device, adev)
+    E, _, H, W = (int(s) for s in sceneCoordinates.shape)
+    rounds = np.zeros(M, np.int32)
+    inl = np.zeros(M, np.int32)
+    ctx.check(ctx.lib.esacb200_refine_poses(ctx.handle, co.ptr, E, H, W, aptr, astride, M, poses6.ctypes.data, int(shiftX),
+                                            int(shiftY), float(focalLength), float(ppointX), float(ppointY),
+                                            float(inlierThreshold), float(maxReproj), int(subSampling),
+                                            rounds.ctypes.data, inl.ctypes.data))
+    return poses6, rounds, inl
+
+
+def set_seed(seed: int, device: int | None = None):
+    context(device).set_seed(seed)
+
+
+def set_option(key: str, value: float, device: int | None = None):
+    context(device).set_option(key, value)
+
+
+def inject_cells(cells, device: int | None = None):
+    context(device).inject_cells(cells)
+
+
+def last_stats(device: int | None = None) -> dict:
+    return context(device).stats()
+
+
+def last_hypotheses(device: int | None = None, losses: bool = False) -> dict:
+    return context(device).hypotheses(losses)

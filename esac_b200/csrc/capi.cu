@@ -1,0 +1,756 @@
+// Host side of libesac_b200.so: context, workspace, stage orchestration, the C ABI of include/esac_b200.h.
+//
+// Orchestration follows esac_forward (esac.cpp:64-190) and esac_backward (esac.cpp:213-511) stage by
+// stage; every stage is a CUDA kernel launched on one stream with no host round trip until the final
+// 68-byte (forward) / 8-byte (backward) result copy.
+#include <cuda_runtime.h>
+#include <stdarg.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <vector>
+
+#include "../../include/esac_b200.h"
+#include "../../include/esac_b200_testhooks.h"
+#include "esac_internal.h"
+#include "esac_rng.cuh"
+
+using namespace esacb200;
+
+namespace {
+
+struct DevBuf {
+    void* p = nullptr;
+    size_t cap = 0;
+    cudaError_t ensure(size_t bytes) {
+        if (bytes <= cap) return cudaSuccess;
+        if (p) cudaFree(p);
+        p = nullptr;
+        cap = 0;
+        size_t want = bytes + bytes / 4 + 256;
+        cudaError_t e = cudaMalloc(&p, want);
+        if (e == cudaSuccess) cap = want;
+        return e;
+    }
+    void release() {
+        if (p) cudaFree(p);
+        p = nullptr;
+        cap = 0;
+    }
+    template <class T>
+    T* as() const { return (T*)p; }
+};
+
+enum { EV_START = 0, EV_H2D, EV_PREP, EV_SAMPLE, EV_FOLD, EV_SCORE, EV_SELECT, EV_REFINE, EV_BWD, EV_END, EV_COUNT };
+
+}  // namespace
+
+struct esacb200_ctx {
+    int device = 0;
+    int sm_count = 0;
+    char dev_name[128] = {0};
+    cudaStream_t own_stream = nullptr;
+    cudaStream_t stream = nullptr;
+    uint64_t seed = 1305;  // thread_rand.h:103
+    uint64_t calls = 0;
+    int max_tries = 1000000;
+    int max_ref_steps = 100;
+    int fixed_seed = 0;
+    int refine_group_opt = 0;
+    int refine_coresident = 0;
+    char err[512] = {0};
+    // workspace
+    DevBuf coords, grads, assign64, assign32, counts, offsets, perm, slot_of, chunks, scalars, centres, poses, poses_ref,
+        cells, tries, posepk, part, scores, probs, stats, contrib, masks, rounds, scratch, barrier, out17, inject,
+        losses, red, hypgrad, job_of, gt;
+    float* h_out = nullptr;  // pinned staging: 32 floats
+    double* h_dbl = nullptr; // pinned staging: 8 doubles
+    int inj_M = 0, inj_T = 0;
+    cudaEvent_t ev[EV_COUNT] = {nullptr};
+    bool ev_used[EV_COUNT] = {false};
+    esacb200_stats st;
+    int last_M = 0;
+    bool last_backward = false;
+};
+
+namespace {
+
+int fail(esacb200_ctx* c, int code, const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(c->err, sizeof(c->err), fmt, ap);
+    va_end(ap);
+    return code;
+}
+
+#define CK(call)                                                                                          \
+    do {                                                                                                  \
+        cudaError_t e__ = (call);                                                                         \
+        if (e__ != cudaSuccess)                                                                           \
+            return fail(ctx, ESACB200_ERR_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e__), \
+                        __FILE__, __LINE__);                                                              \
+    } while (0)
+
+bool is_device_ptr(const void* p) {
+    cudaPointerAttributes a;
+    cudaError_t e = cudaPointerGetAttributes(&a, p);
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        return false;
+    }
+    return a.type == cudaMemoryTypeDevice || a.type == cudaMemoryTypeManaged;
+}
+
+void mark(esacb200_ctx* c, int id) {
+    cudaEventRecord(c->ev[id], c->stream);
+    c->ev_used[id] = true;
+}
+
+float span(esacb200_ctx* c, int a, int b) {
+    if (!c->ev_used[a] || !c->ev_used[b]) return 0.f;
+    float ms = 0.f;
+    if (cudaEventElapsedTime(&ms, c->ev[a], c->ev[b]) != cudaSuccess) {
+        cudaGetLastError();
+        return 0.f;
+    }
+    return ms;
+}
+
+// scalars buffer layout (ints): [0]=n_chunks [1]=work_counter [2]=flags [3]=winner [4]=n_contrib
+enum { S_NCHUNKS = 0, S_WORK, S_FLAGS, S_WINNER, S_NCONTRIB, S_COUNT = 16 };
+
+struct Plan {
+    Problem P;
+    int T, ppt, hc, grid, vec_ok;
+    const float* d_coords;
+    const long long* d_assign;
+    long long assign_stride;
+};
+
+int fill_problem(esacb200_ctx* ctx, Problem& P, int E, int H, int W, int M, int shiftX, int shiftY, float f, float ppx,
+                 float ppy, float tau, float alpha, float beta, float maxReproj, int sub) {
+    if (E <= 0 || H <= 0 || W <= 0 || M <= 0) return fail(ctx, ESACB200_ERR_ARG, "empty tensor (E=%d H=%d W=%d M=%d)", E, H, W, M);
+    if ((long long)H * W > (1ll << 30)) return fail(ctx, ESACB200_ERR_ARG, "coordinate map too large");
+    P.E = E; P.H = H; P.W = W; P.N = H * W; P.M = M;
+    P.shiftX = shiftX; P.shiftY = shiftY; P.sub = sub;
+    P.f = f; P.ppx = ppx; P.ppy = ppy; P.tau = tau; P.alpha = alpha; P.beta = beta; P.max_reproj = maxReproj;
+    return 0;
+}
+
+// Upload (or alias) the inputs and run the prep kernel.
+int stage_inputs(esacb200_ctx* ctx, Plan& pl, const float* coords, const int64_t* assign, int64_t stride) {
+    const Problem& P = pl.P;
+    const size_t cbytes = (size_t)P.E * 3 * P.N * sizeof(float);
+    if (is_device_ptr(coords)) {
+        pl.d_coords = coords;
+    } else {
+        CK(ctx->coords.ensure(cbytes));
+        CK(cudaMemcpyAsync(ctx->coords.p, coords, cbytes, cudaMemcpyHostToDevice, ctx->stream));
+        pl.d_coords = ctx->coords.as<float>();
+    }
+    if (is_device_ptr(assign)) {
+        pl.d_assign = (const long long*)assign;
+        pl.assign_stride = stride;
+    } else {
+        std::vector<long long> tmp((size_t)P.M);
+        for (int h = 0; h < P.M; ++h) tmp[h] = (long long)assign[(long long)h * stride];
+        CK(ctx->assign64.ensure((size_t)P.M * 8));
+        // pageable source: the copy is staged before cudaMemcpyAsync returns, so tmp may die
+        CK(cudaMemcpyAsync(ctx->assign64.p, tmp.data(), (size_t)P.M * 8, cudaMemcpyHostToDevice, ctx->stream));
+        pl.d_assign = ctx->assign64.as<long long>();
+        pl.assign_stride = 1;
+    }
+    mark(ctx, EV_H2D);
+    // scoring launch shape
+    int ppt = 8, hc = 64;
+    const int want = 2 * 2 * ctx->sm_count;
+    auto items = [&](int ppt_, int hc_) {
+        int T = (P.N + score_tile_pixels(ppt_) - 1) / score_tile_pixels(ppt_);
+        int nch = (P.M + hc_ - 1) / hc_ + (P.E > 1 ? P.E / 2 : 0);
+        return (long long)T * nch;
+    };
+    if (items(8, 64) < want) { ppt = 4; hc = 32; }
+    if (ppt == 4 && items(4, 32) < want) { ppt = 2; hc = 16; }
+    pl.ppt = ppt;
+    pl.hc = hc;
+    pl.T = (P.N + score_tile_pixels(ppt) - 1) / score_tile_pixels(ppt);
+    const int max_chunks = (P.M + hc - 1) / hc + P.E;
+    long long it = (long long)pl.T * max_chunks;
+    pl.grid = (int)(it < 2ll * ctx->sm_count ? it : 2ll * ctx->sm_count);
+    const int need_align = ppt >= 4 ? 4 : 2;
+    pl.vec_ok = (P.N % need_align == 0) && (((uintptr_t)pl.d_coords) % (need_align * 4) == 0);
+
+    CK(ctx->assign32.ensure((size_t)P.M * 4));
+    CK(ctx->counts.ensure((size_t)P.E * 4));
+    CK(ctx->offsets.ensure((size_t)(P.E + 1) * 4));
+    CK(ctx->perm.ensure((size_t)P.M * 4));
+    CK(ctx->slot_of.ensure((size_t)P.M * 4));
+    CK(ctx->chunks.ensure((size_t)(P.M + P.E) * sizeof(ChunkDesc)));
+    CK(ctx->scalars.ensure(S_COUNT * 4));
+    CK(ctx->centres.ensure((size_t)P.E * 3 * 4));
+    CK(ctx->poses.ensure((size_t)P.M * sizeof(Pose)));
+    CK(ctx->poses_ref.ensure((size_t)P.M * sizeof(Pose)));
+    CK(ctx->cells.ensure((size_t)P.M * 8 * 4));
+    CK(ctx->tries.ensure((size_t)P.M * 4));
+    CK(ctx->posepk.ensure((size_t)P.M * sizeof(PosePk)));
+    CK(ctx->part.ensure((size_t)P.M * pl.T * 4));
+    CK(ctx->scores.ensure((size_t)P.M * 8));
+    CK(ctx->probs.ensure((size_t)P.M * 8));
+    CK(ctx->stats.ensure(8 * 8));
+    CK(ctx->contrib.ensure((size_t)P.M * 4));
+    CK(ctx->out17.ensure(32 * 4));
+    int* sc = ctx->scalars.as<int>();
+    launch_prep(pl.d_coords, pl.d_assign, pl.assign_stride, P, hc, ctx->assign32.as<int>(), ctx->counts.as<int>(),
+                ctx->offsets.as<int>(), ctx->perm.as<int>(), ctx->slot_of.as<int>(), ctx->chunks.as<ChunkDesc>(),
+                sc + S_NCHUNKS, sc + S_WORK, ctx->centres.as<float>(), sc + S_FLAGS, ctx->stream);
+    ctx->st.kernel_launches += 1;
+    mark(ctx, EV_PREP);
+    return 0;
+}
+
+int run_score(esacb200_ctx* ctx, const Plan& pl) {
+    const Problem& P = pl.P;
+    int* sc = ctx->scalars.as<int>();
+    launch_fold(ctx->poses.as<Pose>(), ctx->perm.as<int>(), ctx->assign32.as<int>(), ctx->centres.as<float>(), P,
+                ctx->posepk.as<PosePk>(), ctx->stream);
+    mark(ctx, EV_FOLD);
+    ScoreArgs a;
+    a.coords = pl.d_coords;
+    a.centres = ctx->centres.as<float>();
+    a.poses = ctx->posepk.as<PosePk>();
+    a.chunks = ctx->chunks.as<ChunkDesc>();
+    a.n_chunks = sc + S_NCHUNKS;
+    a.work_counter = sc + S_WORK;
+    a.part = ctx->part.as<float>();
+    a.P = P;
+    a.T = pl.T;
+    a.hc = pl.hc;
+    const float log2e = 1.4426950408889634f;
+    a.k1 = P.beta * log2e;
+    a.k0 = -P.beta * P.tau * log2e;
+    a.vec_ok = pl.vec_ok;
+    launch_score(a, pl.ppt, pl.grid, ctx->stream);
+    mark(ctx, EV_SCORE);
+    launch_select(ctx->part.as<float>(), ctx->slot_of.as<int>(), P, pl.T, ctx->scores.as<double>(), ctx->probs.as<double>(),
+                  ctx->stats.as<double>(), sc + S_WINNER, ctx->contrib.as<int>(), sc + S_NCONTRIB, ctx->stream);
+    mark(ctx, EV_SELECT);
+    ctx->st.kernel_launches += 3;
+    ctx->st.score_launches += 1;
+    ctx->st.score_ppt = pl.ppt;
+    ctx->st.score_grid = pl.grid;
+    return 0;
+}
+
+int pick_group(esacb200_ctx* ctx, const Problem& P, int jobs_hint) {
+    if (ctx->refine_group_opt > 0) return ctx->refine_group_opt < ctx->refine_coresident ? ctx->refine_group_opt : ctx->refine_coresident;
+    const int words = (P.N + 31) / 32;
+    int g = words / 128;
+    if (g < 1) g = 1;
+    int cap = ctx->refine_coresident / (jobs_hint > 0 ? jobs_hint : 1);
+    if (cap < 1) cap = 1;
+    if (g > cap) g = cap;
+    return g;
+}
+
+// Refinement of `n_jobs` (host count, or device scalar when d_njobs != null) hypotheses listed in d_jobs.
+int run_refine(esacb200_ctx* ctx, const Plan& pl, const Pose* in, Pose* out, const int* d_jobs, const int* d_njobs,
+               int n_jobs_host, int max_jobs, int group) {
+    const Problem& P = pl.P;
+    const int words = (P.N + 31) / 32;
+    int n_groups = ctx->refine_coresident / group;
+    if (n_groups > max_jobs) n_groups = max_jobs;
+    if (n_groups < 1) n_groups = 1;
+    CK(ctx->masks.ensure((size_t)max_jobs * 2 * words * 4));
+    CK(ctx->rounds.ensure((size_t)max_jobs * 2 * 4));
+    CK(ctx->scratch.ensure((size_t)n_groups * group * 2 * 32 * 8));
+    CK(ctx->barrier.ensure((size_t)n_groups * 4));
+    CK(cudaMemsetAsync(ctx->barrier.p, 0, (size_t)n_groups * 4, ctx->stream));
+    RefineArgs a;
+    a.coords = pl.d_coords;
+    a.assign32 = ctx->assign32.as<int>();
+    a.poses_in = in;
+    a.poses_out = out;
+    a.jobs = d_jobs;
+    a.n_jobs = d_njobs;
+    a.n_jobs_host = n_jobs_host;
+    a.masks = ctx->masks.as<uint32_t>();
+    a.mask_words = words;
+    a.rounds = ctx->rounds.as<int>();
+    a.scratch = ctx->scratch.as<double>();
+    a.barrier = ctx->barrier.as<unsigned int>();
+    a.group = group;
+    a.P = P;
+    a.max_ref_steps = ctx->max_ref_steps;
+    launch_refine(a, n_groups, ctx->stream);
+    CK(cudaGetLastError());
+    ctx->st.kernel_launches += 1;
+    ctx->st.refine_group = group;
+    return 0;
+}
+
+void begin_call(esacb200_ctx* ctx) {
+    memset(&ctx->st, 0, sizeof(ctx->st));
+    for (int i = 0; i < EV_COUNT; ++i) ctx->ev_used[i] = false;
+    ctx->err[0] = 0;
+    cudaSetDevice(ctx->device);
+    mark(ctx, EV_START);
+}
+
+void finish_stats(esacb200_ctx* ctx) {
+    esacb200_stats& s = ctx->st;
+    s.ms_h2d = span(ctx, EV_START, EV_H2D);
+    s.ms_prep = span(ctx, EV_H2D, EV_PREP);
+    s.ms_sample = span(ctx, EV_PREP, EV_SAMPLE);
+    s.ms_score = span(ctx, EV_FOLD, EV_SCORE);
+    s.ms_select = span(ctx, EV_SCORE, EV_SELECT);
+    s.ms_refine = span(ctx, EV_SELECT, EV_REFINE);
+    s.ms_backward = span(ctx, EV_REFINE, EV_BWD);
+    s.ms_total = span(ctx, EV_START, EV_END);
+}
+
+uint64_t call_seed(esacb200_ctx* ctx) {
+    uint64_t s = ctx->fixed_seed ? ctx->seed : mix64(ctx->seed + kGold * ctx->calls);
+    if (ctx->calls == 0) s = ctx->seed;
+    ++ctx->calls;
+    return s;
+}
+
+}  // namespace
+
+// =================================================================================================
+extern "C" {
+
+int esacb200_create(int device, esacb200_ctx** out) {
+    if (!out) return ESACB200_ERR_ARG;
+    *out = nullptr;
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess || n <= 0 || device < 0 || device >= n) {
+        cudaGetLastError();
+        return ESACB200_ERR_NO_DEVICE;
+    }
+    esacb200_ctx* ctx = new esacb200_ctx();
+    ctx->device = device;
+    if (cudaSetDevice(device) != cudaSuccess) { delete ctx; return ESACB200_ERR_NO_DEVICE; }
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) { delete ctx; return ESACB200_ERR_CUDA; }
+    ctx->sm_count = prop.multiProcessorCount;
+    snprintf(ctx->dev_name, sizeof(ctx->dev_name), "%s", prop.name);
+    if (cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking) != cudaSuccess) { delete ctx; return ESACB200_ERR_CUDA; }
+    ctx->stream = ctx->own_stream;
+    for (int i = 0; i < EV_COUNT; ++i) cudaEventCreate(&ctx->ev[i]);
+    cudaMallocHost((void**)&ctx->h_out, 32 * sizeof(float));
+    cudaMallocHost((void**)&ctx->h_dbl, 8 * sizeof(double));
+    ctx->refine_coresident = refine_max_coresident_blocks(ctx->sm_count);
+    if (ctx->refine_coresident < 1) ctx->refine_coresident = 1;
+    memset(&ctx->st, 0, sizeof(ctx->st));
+    *out = ctx;
+    return ESACB200_OK;
+}
+
+void esacb200_destroy(esacb200_ctx* ctx) {
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    cudaStreamSynchronize(ctx->stream);
+    DevBuf* bufs[] = {&ctx->coords, &ctx->grads, &ctx->assign64, &ctx->assign32, &ctx->counts, &ctx->offsets, &ctx->perm,
+                      &ctx->slot_of, &ctx->chunks, &ctx->scalars, &ctx->centres, &ctx->poses, &ctx->poses_ref, &ctx->cells,
+                      &ctx->tries, &ctx->posepk, &ctx->part, &ctx->scores, &ctx->probs, &ctx->stats, &ctx->contrib,
+                      &ctx->masks, &ctx->rounds, &ctx->scratch, &ctx->barrier, &ctx->out17, &ctx->inject, &ctx->losses,
+                      &ctx->red, &ctx->hypgrad, &ctx->job_of, &ctx->gt};
+    for (DevBuf* b : bufs) b->release();
+    for (int i = 0; i < EV_COUNT; ++i)
+        if (ctx->ev[i]) cudaEventDestroy(ctx->ev[i]);
+    if (ctx->h_out) cudaFreeHost(ctx->h_out);
+    if (ctx->h_dbl) cudaFreeHost(ctx->h_dbl);
+    if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
+    delete ctx;
+}
+
+const char* esacb200_last_error(const esacb200_ctx* ctx) { return ctx ? ctx->err : "null context"; }
+
+int esacb200_set_stream(esacb200_ctx* ctx, void* s) {
+    if (!ctx) return ESACB200_ERR_ARG;
+    ctx->stream = s ? (cudaStream_t)s : ctx->own_stream;
+    return ESACB200_OK;
+}
+
+int esacb200_set_seed(esacb200_ctx* ctx, uint64_t seed) {
+    if (!ctx) return ESACB200_ERR_ARG;
+    ctx->seed = seed;
+    ctx->calls = 0;
+    return ESACB200_OK;
+}
+
+int esacb200_set_option(esacb200_ctx* ctx, const char* key, double v) {
+    if (!ctx || !key) return ESACB200_ERR_ARG;
+    if (!strcmp(key, "max_tries")) ctx->max_tries = v < 1 ? 1 : (int)v;
+    else if (!strcmp(key, "max_ref_steps")) ctx->max_ref_steps = v < 0 ? 0 : (int)v;
+    else if (!strcmp(key, "fixed_seed")) ctx->fixed_seed = v != 0;
+    else if (!strcmp(key, "refine_group")) ctx->refine_group_opt = (int)v;
+    else return fail(ctx, ESACB200_ERR_ARG, "unknown option '%s'", key);
+    return ESACB200_OK;
+}
+
+int esacb200_inject_cells(esacb200_ctx* ctx, const int32_t* cells, int M, int T) {
+    if (!ctx) return ESACB200_ERR_ARG;
+    cudaSetDevice(ctx->device);
+    if (!cells) { ctx->inj_M = ctx->inj_T = 0; return ESACB200_OK; }
+    if (M <= 0 || T <= 0) return fail(ctx, ESACB200_ERR_ARG, "inject_cells: M and T must be positive");
+    size_t bytes = (size_t)M * T * 8 * 4;
+    CK(ctx->inject.ensure(bytes));
+    CK(cudaMemcpy(ctx->inject.p, cells, bytes, cudaMemcpyHostToDevice));
+    ctx->inj_M = M;
+    ctx->inj_T = T;
+    return ESACB200_OK;
+}
+
+int esacb200_device_info(esacb200_ctx* ctx, int* sm_count, char* name, int name_len) {
+    if (!ctx) return ESACB200_ERR_ARG;
+    if (sm_count) *sm_count = ctx->sm_count;
+    if (name && name_len > 0) snprintf(name, name_len, "%s", ctx->dev_name);
+    return ESACB200_OK;
+}
+
+// -------------------------------------------------------------------------------------------------
+int esacb200_forward(esacb200_ctx* ctx, const float* coords, int E, int H, int W, const int64_t* assign,
+                     int64_t assign_stride, int M, float* out_pose, int shiftX, int shiftY, float f, float ppx,
+                     float ppy, float tau, float alpha, float beta, float maxReproj, int sub, int* out_expert) {
+    if (!ctx) return ESACB200_ERR_ARG;
+    if (!coords || !assign || !out_pose) return fail(ctx, ESACB200_ERR_ARG, "null pointer argument");
+    Plan pl;
+    int rc = fill_problem(ctx, pl.P, E, H, W, M, shiftX, shiftY, f, ppx, ppy, tau, alpha, beta, maxReproj, sub);
+    if (rc) return rc;
+    if ((long long)(W - 1) * (H - 1) < 4) return fail(ctx, ESACB200_ERR_ARG, "map %dx%d too small to draw 4 distinct cells from [0,W-2]x[0,H-2]", W, H);
+    if (ctx->inj_M && ctx->inj_M != M) return fail(ctx, ESACB200_ERR_ARG, "injected cells are for M=%d, call has M=%d", ctx->inj_M, M);
+    begin_call(ctx);
+    rc = stage_inputs(ctx, pl, coords, assign, assign_stride);
+    if (rc) return rc;
+    const Problem& P = pl.P;
+    int* sc = ctx->scalars.as<int>();
+    const uint64_t seed = call_seed(ctx);
+    launch_sample(pl.d_coords, ctx->assign32.as<int>(), P, seed, ctx->max_tries, ctx->inj_M ? ctx->inject.as<int>() : nullptr,
+                  ctx->inj_T, ctx->poses.as<Pose>(), ctx->cells.as<int>(), ctx->tries.as<int>(), ctx->stream);
+    ctx->st.kernel_launches += 1;
+    mark(ctx, EV_SAMPLE);
+    rc = run_score(ctx, pl);
+    if (rc) return rc;
+    const int group = pick_group(ctx, P, 1);
+    rc = run_refine(ctx, pl, ctx->poses.as<Pose>(), ctx->poses_ref.as<Pose>(), sc + S_WINNER, nullptr, 1, 1, group);
+    if (rc) return rc;
+    mark(ctx, EV_REFINE);
+    launch_finish_forward(ctx->poses_ref.as<Pose>(), sc + S_WINNER, ctx->assign32.as<int>(), ctx->out17.as<float>(), ctx->stream);
+    ctx->st.kernel_launches += 1;
+    CK(cudaMemcpyAsync(ctx->h_out, ctx->out17.p, 17 * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaMemcpyAsync(ctx->h_out + 20, sc, 8 * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaMemcpyAsync(ctx->h_dbl, ctx->stats.p, 3 * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaMemcpyAsync(ctx->h_dbl + 4, ctx->rounds.p, 2 * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    if (is_device_ptr(out_pose)) CK(cudaMemcpyAsync(out_pose, ctx->out17.p, 16 * sizeof(float), cudaMemcpyDeviceToDevice, ctx->stream));
+    mark(ctx, EV_END);
+    CK(cudaStreamSynchronize(ctx->stream));
+    CK(cudaGetLastError());
+    const int* hs = (const int*)(ctx->h_out + 20);
+    if (hs[S_FLAGS]) return fail(ctx, ESACB200_ERR_ARG, "hypAssignment holds an expert index outside [0, %d)", E);
+    if (!is_device_ptr(out_pose)) memcpy(out_pose, ctx->h_out, 16 * sizeof(float));
+    if (out_expert) *out_expert = (int)ctx->h_out[16];
+    ctx->st.M = M;
+    ctx->st.winner = hs[S_WINNER];
+    ctx->st.n_contrib = hs[S_NCONTRIB];
+    ctx->st.entropy = ctx->h_dbl[0];
+    ctx->st.refine_rounds = ((const int*)(ctx->h_dbl + 4))[0];
+    ctx->last_M = M;
+    ctx->last_backward = false;
+    finish_stats(ctx);
+    ctx->inj_M = ctx->inj_T = 0;
+    return ESACB200_OK;
+}
+
+// -------------------------------------------------------------------------------------------------
+int esacb200_score_poses(esacb200_ctx* ctx, const float* coords, int E, int H, int W, const int64_t* assign,
+                         int64_t assign_stride, int M, const double* poses6, int shiftX, int shiftY, float f, float ppx,
+                         float ppy, float tau, float alpha, float beta, float maxReproj, int sub, double* out_scores) {
+    if (!ctx) return ESACB200_ERR_ARG;
+    if (!coords || !assign || !poses6 || !out_scores) return fail(ctx, ESACB200_ERR_ARG, "null pointer argument");
+    Plan pl;
+    int rc = fill_problem(ctx, pl.P, E, H, W, M, shiftX, shiftY, f, ppx, ppy, tau, alpha, beta, maxReproj, sub);
+    if (rc) return rc;
+    begin_call(ctx);
+    rc = stage_inputs(ctx, pl, coords, assign, assign_stride);
+    if (rc) return rc;
+    CK(cudaMemcpyAsync(ctx->poses.p, poses6, (size_t)M * sizeof(Pose), cudaMemcpyHostToDevice, ctx->stream));
+    mark(ctx, EV_SAMPLE);
+    rc = run_score(ctx, pl);
+    if (rc) return rc;
+    CK(cudaMemcpyAsync(out_scores, ctx->scores.p, (size_t)M * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaMemcpyAsync(ctx->h_out + 20, ctx->scalars.p, 8 * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    mark(ctx, EV_END);
+    CK(cudaStreamSynchronize(ctx->stream));
+    CK(cudaGetLastError());
+    const int* hs = (const int*)(ctx->h_out + 20);
+    if (hs[S_FLAGS]) return fail(ctx, ESACB200_ERR_ARG, "hypAssignment holds an expert index outside [0, %d)", E);
+    ctx->st.M = M;
+    ctx->st.winner = hs[S_WINNER];
+    ctx->st.n_contrib = hs[S_NCONTRIB];
+    ctx->last_M = M;
+    ctx->last_backward = false;
+    finish_stats(ctx);
+    return ESACB200_OK;
+}
+
+// -------------------------------------------------------------------------------------------------
+int esacb200_refine_poses(esacb200_ctx* ctx, const float* coords, int E, int H, int W, const int64_t* assign,
+                          int64_t assign_stride, int M, double* poses6, int shiftX, int shiftY, float f, float ppx,
+                          float ppy, float tau, float maxReproj, int sub, int* out_rounds, int* out_inliers) {
+    if (!ctx) return ESACB200_ERR_ARG;
+    if (!coords || !assign || !poses6) return fail(ctx, ESACB200_ERR_ARG, "null pointer argument");
+    Plan pl;
+    int rc = fill_problem(ctx, pl.P, E, H, W, M, shiftX, shiftY, f, ppx, ppy, tau, 100.f, 0.5f, maxReproj, sub);
+    if (rc) return rc;
+    begin_call(ctx);
+    rc = stage_inputs(ctx, pl, coords, assign, assign_stride);
+    if (rc) return rc;
+    CK(cudaMemcpyAsync(ctx->poses.p, poses6, (size_t)M * sizeof(Pose), cudaMemcpyHostToDevice, ctx->stream));
+    std::vector<int> jobs((size_t)M);
+    for (int i = 0; i < M; ++i) jobs[i] = i;
+    CK(cudaMemcpyAsync(ctx->contrib.p, jobs.data(), (size_t)M * 4, cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    const int group = pick_group(ctx, pl.P, M);
+    mark(ctx, EV_SELECT);
+    rc = run_refine(ctx, pl, ctx->poses.as<Pose>(), ctx->poses_ref.as<Pose>(), ctx->contrib.as<int>(), nullptr, M, M, group);
+    if (rc) return rc;
+    mark(ctx, EV_REFINE);
+    mark(ctx, EV_END);
+    CK(cudaStreamSynchronize(ctx->stream));
+    CK(cudaGetLastError());
+    CK(cudaMemcpy(poses6, ctx->poses_ref.p, (size_t)M * sizeof(Pose), cudaMemcpyDeviceToHost));
+    std::vector<int> rr((size_t)M * 2);
+    CK(cudaMemcpy(rr.data(), ctx->rounds.p, (size_t)M * 8, cudaMemcpyDeviceToHost));
+    const int words = (pl.P.N + 31) / 32;
+    std::vector<uint32_t> mk;
+    if (out_inliers) {
+        mk.resize((size_t)M * 2 * words);
+        CK(cudaMemcpy(mk.data(), ctx->masks.p, mk.size() * 4, cudaMemcpyDeviceToHost));
+    }
+    for (int i = 0; i < M; ++i) {
+        if (out_rounds) out_rounds[i] = rr[2 * i];
+        if (out_inliers) {
+            int c = 0;
+            if (rr[2 * i] > 0) {
+                const uint32_t* m = mk.data() + ((size_t)i * 2 + rr[2 * i + 1]) * words;
+                for (int w = 0; w < words; ++w) c += __builtin_popcount(m[w]);
+            }
+            out_inliers[i] = c;
+        }
+    }
+    ctx->st.M = M;
+    ctx->last_M = M;
+    finish_stats(ctx);
+    return ESACB200_OK;
+}
+
+
+// -------------------------------------------------------------------------------------------------
+int esacb200_backward(esacb200_ctx* ctx, const float* coords, float* grads, int E, int H, int W, const int64_t* assign,
+                      int64_t assign_stride, int M, const float* gt_pose, float wRot, float wTrans, float cut, int shiftX,
+                      int shiftY, float f, float ppx, float ppy, float tau, float alpha, float beta, float maxReproj, int sub,
+                      double* out_loss) {
+    if (!ctx) return ESACB200_ERR_ARG;
+    if (!coords || !assign || !grads || !gt_pose) return fail(ctx, ESACB200_ERR_ARG, "null pointer argument");
+    Plan pl;
+    int rc = fill_problem(ctx, pl.P, E, H, W, M, shiftX, shiftY, f, ppx, ppy, tau, alpha, beta, maxReproj, sub);
+    if (rc) return rc;
+    if ((long long)(W - 1) * (H - 1) < 4) return fail(ctx, ESACB200_ERR_ARG, "map %dx%d too small to draw 4 distinct cells from [0,W-2]x[0,H-2]", W, H);
+    if (ctx->inj_M && ctx->inj_M != M) return fail(ctx, ESACB200_ERR_ARG, "injected cells are for M=%d, call has M=%d", ctx->inj_M, M);
+    begin_call(ctx);
+    const Problem& P = pl.P;
+    const size_t cbytes = (size_t)P.E * 3 * P.N * sizeof(float);
+    float* d_grads = grads;
+    const bool grads_on_host = !is_device_ptr(grads);
+    if (grads_on_host) {
+        CK(ctx->grads.ensure(cbytes));
+        CK(cudaMemcpyAsync(ctx->grads.p, grads, cbytes, cudaMemcpyHostToDevice, ctx->stream));
+        d_grads = ctx->grads.as<float>();
+    }
+    rc = stage_inputs(ctx, pl, coords, assign, assign_stride);
+    if (rc) return rc;
+    int* sc = ctx->scalars.as<int>();
+    const uint64_t seed = call_seed(ctx);
+    launch_sample(pl.d_coords, ctx->assign32.as<int>(), P, seed, ctx->max_tries, ctx->inj_M ? ctx->inject.as<int>() : nullptr,
+                  ctx->inj_T, ctx->poses.as<Pose>(), ctx->cells.as<int>(), ctx->tries.as<int>(), ctx->stream);
+    ctx->st.kernel_launches += 1;
+    mark(ctx, EV_SAMPLE);
+    rc = run_score(ctx, pl);
+    if (rc) return rc;
+    // refHyps = initHyps for everything below PROB_THRESH (esac.cpp:331-334)
+    CK(cudaMemcpyAsync(ctx->poses_ref.p, ctx->poses.p, (size_t)M * sizeof(Pose), cudaMemcpyDeviceToDevice, ctx->stream));
+    int group = pick_group(ctx, P, 8);
+    rc = run_refine(ctx, pl, ctx->poses.as<Pose>(), ctx->poses_ref.as<Pose>(), ctx->contrib.as<int>(), sc + S_NCONTRIB, 0, M, group);
+    if (rc) return rc;
+    mark(ctx, EV_REFINE);
+    const int tiles = bwd_tiles(P.N);
+    CK(ctx->losses.ensure((size_t)M * 8));
+    CK(ctx->red.ensure((size_t)M * tiles * bwd_red_vals() * 8));
+    CK(ctx->hypgrad.ensure((size_t)M * bwd_hypgrad_bytes()));
+    CK(ctx->job_of.ensure((size_t)(M > E ? M : E) * 4));
+    BwdArgs b;
+    b.coords = pl.d_coords;
+    b.grads = d_grads;
+    b.assign32 = ctx->assign32.as<int>();
+    b.perm = ctx->perm.as<int>();
+    b.counts = ctx->counts.as<int>();
+    b.offsets = ctx->offsets.as<int>();
+    b.init = ctx->poses.as<Pose>();
+    b.ref = ctx->poses_ref.as<Pose>();
+    b.cells = ctx->cells.as<int>();
+    b.probs = ctx->probs.as<double>();
+    b.contrib = ctx->contrib.as<int>();
+    b.n_contrib = sc + S_NCONTRIB;
+    b.job_of = ctx->job_of.as<int>();
+    b.masks = ctx->masks.as<uint32_t>();
+    b.mask_words = (P.N + 31) / 32;
+    b.rounds = ctx->rounds.as<int>();
+    b.losses = ctx->losses.as<double>();
+    b.out_loss = ctx->stats.as<double>() + 4;
+    b.red = ctx->red.as<double>();
+    b.hyp_grad = ctx->hypgrad.p;
+    if (is_device_ptr(gt_pose)) {
+        CK(cudaMemcpyAsync(ctx->h_out, gt_pose, 16 * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
+        CK(cudaStreamSynchronize(ctx->stream));
+        memcpy(b.gt, ctx->h_out, 16 * sizeof(float));
+    } else {
+        memcpy(b.gt, gt_pose, 16 * sizeof(float));
+    }
+    b.wRot = wRot; b.wTrans = wTrans; b.cut = cut;
+    b.P = P;
+    launch_backward(b, M, ctx->stream);
+    CK(cudaGetLastError());
+    ctx->st.kernel_launches += 5;
+    mark(ctx, EV_BWD);
+    if (grads_on_host) CK(cudaMemcpyAsync(grads, d_grads, cbytes, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaMemcpyAsync(ctx->h_out + 20, sc, 8 * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaMemcpyAsync(ctx->h_dbl, ctx->stats.p, 5 * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    mark(ctx, EV_END);
+    CK(cudaStreamSynchronize(ctx->stream));
+    CK(cudaGetLastError());
+    const int* hs = (const int*)(ctx->h_out + 20);
+    if (hs[S_FLAGS]) return fail(ctx, ESACB200_ERR_ARG, "hypAssignment holds an expert index outside [0, %d)", E);
+    if (out_loss) *out_loss = ctx->h_dbl[4];
+    ctx->st.M = M;
+    ctx->st.winner = hs[S_WINNER];
+    ctx->st.n_contrib = hs[S_NCONTRIB];
+    ctx->st.entropy = ctx->h_dbl[0];
+    ctx->st.expected_loss = ctx->h_dbl[4];
+    ctx->last_M = M;
+    ctx->last_backward = true;
+    finish_stats(ctx);
+    ctx->inj_M = ctx->inj_T = 0;
+    return ESACB200_OK;
+}
+
+int esacb200_get_stats(esacb200_ctx* ctx, esacb200_stats* out) {
+    if (!ctx || !out) return ESACB200_ERR_ARG;
+    *out = ctx->st;
+    return ESACB200_OK;
+}
+
+int esacb200_get_hypotheses(esacb200_ctx* ctx, double* poses6, int32_t* cells, int32_t* tries, double* scores,
+                            double* probs, double* refined6, double* losses) {
+    if (!ctx) return ESACB200_ERR_ARG;
+    const int M = ctx->last_M;
+    if (M <= 0) return fail(ctx, ESACB200_ERR_ARG, "no previous call");
+    cudaSetDevice(ctx->device);
+    if (poses6) CK(cudaMemcpy(poses6, ctx->poses.p, (size_t)M * sizeof(Pose), cudaMemcpyDeviceToHost));
+    if (cells) CK(cudaMemcpy(cells, ctx->cells.p, (size_t)M * 32, cudaMemcpyDeviceToHost));
+    if (tries) CK(cudaMemcpy(tries, ctx->tries.p, (size_t)M * 4, cudaMemcpyDeviceToHost));
+    if (scores) CK(cudaMemcpy(scores, ctx->scores.p, (size_t)M * 8, cudaMemcpyDeviceToHost));
+    if (probs) CK(cudaMemcpy(probs, ctx->probs.p, (size_t)M * 8, cudaMemcpyDeviceToHost));
+    if (refined6) CK(cudaMemcpy(refined6, ctx->poses_ref.p, (size_t)M * sizeof(Pose), cudaMemcpyDeviceToHost));
+    if (losses) {
+        if (!ctx->last_backward) return fail(ctx, ESACB200_ERR_ARG, "losses exist only after backward");
+        CK(cudaMemcpy(losses, ctx->losses.p, (size_t)M * 8, cudaMemcpyDeviceToHost));
+    }
+    return ESACB200_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// host test hooks (esac_b200_testhooks.h)
+// ------------------------------------------------------------------------------------------------
+void esacb200_host_rodrigues(const double r[3], double R[9], double J[27]) { rodrigues_v2m(r, R, J); }
+void esacb200_host_rodrigues_inv(const double R[9], double r[3]) { rodrigues_m2v(R, r); }
+
+int esacb200_host_p3p_all(const double* y9, const double* x9, double* Rs36, double* ts12) {
+    double y[3][3], x[3][3], Rs[4][9], ts[4][3];
+    for (int i = 0; i < 3; ++i)
+        for (int c = 0; c < 3; ++c) { y[i][c] = y9[i * 3 + c]; x[i][c] = x9[i * 3 + c]; }
+    int n = p3p_solve(y, x, Rs, ts);
+    for (int s = 0; s < n; ++s) {
+        for (int c = 0; c < 9; ++c) Rs36[s * 9 + c] = Rs[s][c];
+        for (int c = 0; c < 3; ++c) ts12[s * 3 + c] = ts[s][c];
+    }
+    return n;
+}
+
+int esacb200_host_p3p_pose(const float* obj12, const float* img8, float f, float ppx, float ppy, float tau, double* pose6,
+                           int* gate) {
+    float obj[4][3], img[4][2];
+    for (int i = 0; i < 4; ++i) {
+        for (int c = 0; c < 3; ++c) obj[i][c] = obj12[i * 3 + c];
+        for (int c = 0; c < 2; ++c) img[i][c] = img8[i * 2 + c];
+    }
+    Pose p;
+    bool ok = p3p_pose(obj, img, (double)f, (double)ppx, (double)ppy, p);
+    if (gate) *gate = 0;
+    if (!ok) { for (int i = 0; i < 6; ++i) pose6[i] = 0; return 0; }
+    for (int i = 0; i < 3; ++i) { pose6[i] = p.r[i]; pose6[3 + i] = p.t[i]; }
+    if (gate) *gate = minimal_set_gate(obj, img, p, (double)f, (double)ppx, (double)ppy, tau) ? 1 : 0;
+    return 1;
+}
+
+void esacb200_host_project(const double pose6[6], float f, float ppx, float ppy, const float X[3], float uv_f[2],
+                           double uv[2], double J12[12]) {
+    double R[9], dRdr[27];
+    rodrigues_v2m(pose6, R, dRdr);
+    project_point_f(R, pose6 + 3, (double)f, (double)ppx, (double)ppy, X[0], X[1], X[2], uv_f[0], uv_f[1]);
+    double Ju[6], Jv[6];
+    project_point_jac(R, pose6 + 3, dRdr, (double)f, (double)ppx, (double)ppy, (double)X[0], (double)X[1], (double)X[2], uv[0],
+                      uv[1], Ju, Jv);
+    for (int i = 0; i < 6; ++i) { J12[i] = Ju[i]; J12[6 + i] = Jv[i]; }
+}
+
+double esacb200_host_loss(const double* T1, const double* T2, double wRot, double wTrans, double cut) {
+    return pose_loss(T1, T2, wRot, wTrans, cut);
+}
+
+void esacb200_host_dloss(const double est6[6], const double gt6[6], double wRot, double wTrans, double cut, double out6[6]) {
+    Pose a, b;
+    for (int i = 0; i < 3; ++i) { a.r[i] = est6[i]; a.t[i] = est6[3 + i]; b.r[i] = gt6[i]; b.t[i] = gt6[3 + i]; }
+    pose_dloss(a, b, wRot, wTrans, cut, out6);
+}
+
+void esacb200_host_pose2trans(const double pose6[6], double T16[16]) {
+    Pose a;
+    for (int i = 0; i < 3; ++i) { a.r[i] = pose6[i]; a.t[i] = pose6[3 + i]; }
+    pose2trans(a, T16);
+}
+
+void esacb200_host_trans2pose(const double T16[16], double pose6[6]) {
+    Pose a;
+    trans2pose(T16, a);
+    for (int i = 0; i < 3; ++i) { pose6[i] = a.r[i]; pose6[3 + i] = a.t[i]; }
+}
+
+void esacb200_host_dprojectdobj(const float pt[2], const float obj[3], const double pose6[6], float f, float ppx, float ppy,
+                                float maxReproj, double out3[3]) {
+    double R[9];
+    rodrigues_v2m(pose6, R, nullptr);
+    d_project_d_obj(pt[0], pt[1], obj[0], obj[1], obj[2], R, pose6 + 3, (double)f, (double)ppx, (double)ppy, (double)maxReproj, out3);
+}
+
+void esacb200_host_pinv6(const double A[36], double out[36]) { pinv_sym6(A, out); }
+
+void esacb200_host_draw_cells(uint64_t seed, uint32_t h, uint32_t t, int W, int H, int32_t* cells8) {
+    int cx[4], cy[4];
+    draw_minimal_set(seed, h, t, W, H, cx, cy);
+    for (int j = 0; j < 4; ++j) { cells8[2 * j] = cx[j]; cells8[2 * j + 1] = cy[j]; }
+}
+
+}  // extern "C"

@@ -1,0 +1,125 @@
+// Internal declarations shared by the translation units of libesac_b200.so.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "esac_geom.cuh"
+
+namespace esacb200 {
+
+// Per-call problem description (esac.cpp:64-77 arguments + tensor sizes).
+struct Problem {
+    int E, H, W, N, M;
+    int shiftX, shiftY, sub;
+    float f, ppx, ppy;
+    float tau, alpha, beta, max_reproj;
+};
+
+// Hypotheses of one expert are contiguous in "sorted slot" order (stable by hypothesis index);
+// a chunk is <= kMaxChunk consecutive slots of one expert: the unit the scoring kernel pairs with a
+// pixel tile.
+constexpr int kMaxChunk = 64;
+struct ChunkDesc {
+    int expert;
+    int slot0;
+    int count;
+    int pad;
+};
+
+// Folded fp32 pose for the scoring kernel: rows of diag(f,f,1)*R and diag(f,f,1)*(R*c + t), every
+// value stored twice so one LDS.128 yields two aligned f32x2 operands.
+struct PosePk {
+    float4 v[6];
+};
+
+struct ScoreArgs {
+    const float* coords;     // [E,3,N]
+    const float* centres;    // [E,3]
+    const PosePk* poses;     // [M] sorted slots
+    const ChunkDesc* chunks;
+    const int* n_chunks;     // device scalar
+    int* work_counter;       // device scalar, zeroed by the prep kernel
+    float* part;             // [M, T] partial soft-inlier sums (slot-major)
+    Problem P;
+    int T;                   // pixel tiles per plane
+    int hc;                  // hypotheses per chunk used when building the chunk table
+    float k1, k0;            // beta*log2(e), -beta*tau*log2(e)
+    int vec_ok;              // planes are 16-byte aligned and N % 4 == 0
+};
+
+// --- score.cu -----------------------------------------------------------------------------
+// prep: int64 strided assignment -> int32, per-expert histogram / offsets / stable permutation,
+// chunk table, work counter reset, plane centres.  flags[0] != 0 on a bad expert index.
+void launch_prep(const float* coords, const long long* assign, long long assign_stride, const Problem& P,
+                 int hc, int* assign32, int* counts, int* offsets, int* perm, int* slot_of, ChunkDesc* chunks,
+                 int* n_chunks, int* work_counter, float* centres, int* flags, cudaStream_t st);
+void launch_fold(const Pose* poses, const int* perm, const int* assign32, const float* centres, const Problem& P,
+                 PosePk* out, cudaStream_t st);
+int score_tile_pixels(int ppt);
+void launch_score(const ScoreArgs& a, int ppt, int grid, cudaStream_t st);
+// scores[h] = (alpha/W/H) * sum_tiles part ; softmax ; entropy ; argmax ; contributing list
+void launch_select(const float* part, const int* slot_of, const Problem& P, int T, double* scores, double* probs,
+                   double* stats /* [0]=entropy [1]=winner [2]=n_contrib */, int* winner, int* contrib,
+                   int* n_contrib, cudaStream_t st);
+
+// --- hyp.cu -------------------------------------------------------------------------------
+void launch_sample(const float* coords, const int* assign32, const Problem& P, uint64_t seed, int max_tries,
+                   const int* injected, int inj_T, Pose* poses, int* cells, int* tries, cudaStream_t st);
+
+// --- refine.cu ----------------------------------------------------------------------------
+// Refines poses_in[jobs[j]] -> poses_out[jobs[j]] for j < *n_jobs (device scalar) or n_jobs_host.
+// masks: [job][ceil(N/32)] final inlier bit masks (may be null), rounds: [job] accepted rounds.
+struct RefineArgs {
+    const float* coords;
+    const int* assign32;
+    const Pose* poses_in;
+    Pose* poses_out;
+    const int* jobs;
+    const int* n_jobs;       // device scalar (null -> n_jobs_host)
+    int n_jobs_host;
+    uint32_t* masks;
+    int mask_words;          // words per job
+    int* rounds;
+    double* scratch;         // cross-CTA reduction slots
+    unsigned int* barrier;   // cross-CTA barrier counters, zeroed before launch
+    int group;               // CTAs cooperating on one job
+    Problem P;
+    int max_ref_steps;
+};
+void launch_refine(const RefineArgs& a, int n_groups, cudaStream_t st);
+int refine_max_coresident_blocks(int sm_count);
+// camera->world 4x4 float of poses[*idx] + expert id, packed for one D2H copy: out[0..15], out[16]=expert
+void launch_finish_forward(const Pose* poses, const int* winner, const int* assign32, float* out17, cudaStream_t st);
+
+// --- bwd.cu -------------------------------------------------------------------------------
+struct BwdArgs {
+    const float* coords;
+    float* grads;            // [E,3,N] accumulated in place
+    const int* assign32;
+    const int* perm;         // slot -> hyp
+    const int* counts;
+    const int* offsets;
+    const Pose* init;        // [M]
+    const Pose* ref;         // [M] (== init for non-contributing)
+    const int* cells;        // [M,4,2]
+    const double* probs;     // [M]
+    const int* contrib;      // contributing hypothesis ids (ascending)
+    const int* n_contrib;    // device scalar
+    const int* job_of;       // [M] hypothesis -> job index (or -1)
+    const uint32_t* masks;
+    int mask_words;
+    const int* rounds;       // [job]
+    double* losses;          // [M]
+    double* out_loss;        // device scalar: expected loss
+    double* red;             // [job][tiles][kRedVals] partial reductions
+    void* hyp_grad;          // [job] HypGrad records
+    float gt[16];
+    float wRot, wTrans, cut;
+    Problem P;
+};
+void launch_backward(const BwdArgs& a, int max_jobs, cudaStream_t st);
+size_t bwd_hypgrad_bytes();
+int bwd_red_vals();
+int bwd_tiles(int N);
+
+}  // namespace esacb200

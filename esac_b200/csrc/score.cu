@@ -1,0 +1,377 @@
+// Reprojection + soft-inlier scoring (the roofline kernel) and its bookkeeping kernels.
+//
+// Replaces, for all M hypotheses at once, the reference's per-hypothesis CPU loop
+//   getReproErrs (no-Jacobian path)  esac_util.h:274-318,355-362   called from esac.cpp:131-140 / 295-305
+//   getHypScores                      esac_util.h:235-260           called from esac.cpp:143 / 308
+//   softMax / entropy / draw          esac_util.h:461-530           called from esac.cpp:153-155 / 318-319
+//
+// Layout: hypotheses are grouped by expert (stable by index), cut into chunks of <= kMaxChunk; a work
+// item is (chunk, pixel tile).  A CTA keeps its tile's pixels in registers (re-centred coordinates plus
+// the principal-point offset of each cell, two pixels per f32x2 lane pair) and streams the chunk's
+// folded poses from shared memory, so each coordinate plane is read from HBM/L2 once per chunk instead
+// of once per hypothesis.  Per pixel-hypothesis: 9 FFMA for R*X+t, then
+//   err = |p| / |z|,  p = (xc + (cx-px) z, yc + (cy-py) z)   ->  err = num * rsqrt(num * z^2)
+//   w   = 1 / (1 + 2^(k1*min(err,maxReproj) + k0))           ==  1 - sigmoid(beta*(err - tau))
+// i.e. 3 MUFU (rsq, ex2, rcp) and ~20 fp32-pipe ops issued as FFMA2/FMUL2/FADD2.
+#include "esac_internal.h"
+
+namespace esacb200 {
+
+constexpr int kScoreThreads = 256;
+
+// ---------------------------------------------------------------------------------------------
+// prep
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(1024) prep_kernel(const float* __restrict__ coords, const long long* __restrict__ assign,
+                                                    long long stride, Problem P, int hc, int* assign32, int* counts,
+                                                    int* offsets, int* perm, int* slot_of, ChunkDesc* chunks,
+                                                    int* n_chunks, int* work_counter, float* centres, int* flags) {
+    const int tid = threadIdx.x;
+    if (blockIdx.x == 0) {
+        if (tid == 0) { *work_counter = 0; flags[0] = 0; }
+        for (int e = tid; e < P.E; e += blockDim.x) counts[e] = 0;
+        __syncthreads();
+        for (int h = tid; h < P.M; h += blockDim.x) {
+            long long e = assign[(long long)h * stride];
+            if (e < 0 || e >= P.E) { flags[0] = 1; e = 0; }
+            assign32[h] = (int)e;
+            atomicAdd(&counts[(int)e], 1);
+        }
+        __syncthreads();
+        if (tid == 0) {
+            int acc = 0, nc = 0;
+            for (int e = 0; e < P.E; ++e) {
+                offsets[e] = acc;
+                for (int s = 0; s < counts[e]; s += hc) {
+                    ChunkDesc c;
+                    c.expert = e; c.slot0 = acc + s; c.count = min(hc, counts[e] - s); c.pad = 0;
+                    chunks[nc++] = c;
+                }
+                acc += counts[e];
+            }
+            offsets[P.E] = acc;
+            *n_chunks = nc;
+        }
+        __syncthreads();
+        // stable permutation: thread e walks the hypotheses in order
+        for (int e = tid; e < P.E; e += blockDim.x) {
+            if (counts[e] == 0) continue;
+            int pos = offsets[e];
+            for (int h = 0; h < P.M; ++h)
+                if (assign32[h] == e) { perm[pos] = h; slot_of[h] = pos; ++pos; }
+        }
+    } else {
+        // plane centre: mean of a strided sample (only conditions the fp32 arithmetic)
+        const int e = blockIdx.x - 1;
+        const float* pl = coords + (size_t)e * 3 * P.N;
+        const int ns = min(P.N, 4096);
+        const int step = max(1, P.N / ns);
+        float sx = 0, sy = 0, sz = 0, cnt = 0;
+        for (int i = tid; i < ns; i += blockDim.x) {
+            int p = min(i * step, P.N - 1);
+            float x = pl[p], y = pl[P.N + p], z = pl[2 * P.N + p];
+            if (isfinite(x) && isfinite(y) && isfinite(z) && fabsf(x) < 1e18f && fabsf(y) < 1e18f && fabsf(z) < 1e18f) {
+                sx += x; sy += y; sz += z; cnt += 1;
+            }
+        }
+        __shared__ float red[4][32];
+        for (int o = 16; o; o >>= 1) {
+            sx += __shfl_xor_sync(0xffffffffu, sx, o);
+            sy += __shfl_xor_sync(0xffffffffu, sy, o);
+            sz += __shfl_xor_sync(0xffffffffu, sz, o);
+            cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
+        }
+        if ((tid & 31) == 0) { red[0][tid >> 5] = sx; red[1][tid >> 5] = sy; red[2][tid >> 5] = sz; red[3][tid >> 5] = cnt; }
+        __syncthreads();
+        if (tid == 0) {
+            float a = 0, b = 0, c = 0, n = 0;
+            for (int w = 0; w < (int)(blockDim.x >> 5); ++w) { a += red[0][w]; b += red[1][w]; c += red[2][w]; n += red[3][w]; }
+            float inv = n > 0 ? 1.f / n : 0.f;
+            centres[e * 3 + 0] = a * inv; centres[e * 3 + 1] = b * inv; centres[e * 3 + 2] = c * inv;
+        }
+    }
+}
+
+void launch_prep(const float* coords, const long long* assign, long long assign_stride, const Problem& P, int hc,
+                 int* assign32, int* counts, int* offsets, int* perm, int* slot_of, ChunkDesc* chunks, int* n_chunks,
+                 int* work_counter, float* centres, int* flags, cudaStream_t st) {
+    prep_kernel<<<1 + P.E, 1024, 0, st>>>(coords, assign, assign_stride, P, hc, assign32, counts, offsets, perm, slot_of,
+                                          chunks, n_chunks, work_counter, centres, flags);
+}
+
+// ---------------------------------------------------------------------------------------------
+// fold: (rvec, tvec) fp64 -> fp32 rows of diag(f,f,1) R and diag(f,f,1)(R c + t), slot order
+// ---------------------------------------------------------------------------------------------
+__global__ void fold_kernel(const Pose* __restrict__ poses, const int* __restrict__ perm, const int* __restrict__ assign32,
+                            const float* __restrict__ centres, Problem P, PosePk* __restrict__ out) {
+    int s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= P.M) return;
+    int h = perm[s];
+    int e = assign32[h];
+    Pose p = poses[h];
+    double R[9];
+    rodrigues_v2m(p.r, R, nullptr);
+    double c[3] = {(double)centres[e * 3], (double)centres[e * 3 + 1], (double)centres[e * 3 + 2]};
+    double f = (double)P.f;
+    float A[12];
+    for (int r = 0; r < 3; ++r) {
+        double sc = r < 2 ? f : 1.0;
+        double b = R[r * 3] * c[0] + R[r * 3 + 1] * c[1] + R[r * 3 + 2] * c[2] + p.t[r];
+        A[r * 4 + 0] = (float)(sc * R[r * 3 + 0]);
+        A[r * 4 + 1] = (float)(sc * R[r * 3 + 1]);
+        A[r * 4 + 2] = (float)(sc * R[r * 3 + 2]);
+        A[r * 4 + 3] = (float)(sc * b);
+    }
+    PosePk pk;
+    for (int r = 0; r < 3; ++r) {
+        pk.v[r * 2 + 0] = make_float4(A[r * 4 + 0], A[r * 4 + 0], A[r * 4 + 1], A[r * 4 + 1]);
+        pk.v[r * 2 + 1] = make_float4(A[r * 4 + 2], A[r * 4 + 2], A[r * 4 + 3], A[r * 4 + 3]);
+    }
+    out[s] = pk;
+}
+
+void launch_fold(const Pose* poses, const int* perm, const int* assign32, const float* centres, const Problem& P,
+                 PosePk* out, cudaStream_t st) {
+    fold_kernel<<<(P.M + 127) / 128, 128, 0, st>>>(poses, perm, assign32, centres, P, out);
+}
+
+// ---------------------------------------------------------------------------------------------
+// scoring
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ float mufu_rsq(float x) {
+    float y;
+    asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+__device__ __forceinline__ float mufu_ex2(float x) {
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+__device__ __forceinline__ float mufu_rcp(float x) {
+    float y;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+__device__ __forceinline__ float2 lo2(const float4& v) { return make_float2(v.x, v.y); }
+__device__ __forceinline__ float2 hi2(const float4& v) { return make_float2(v.z, v.w); }
+
+template <int PPT, bool TAIL>
+__device__ __forceinline__ void score_item(const ScoreArgs& a, const ChunkDesc cd, const int tile, const float4* sPose,
+                                           float (*sWarp)[kMaxChunk]) {
+    constexpr int NP = PPT / 2;                 // pixel pairs per thread
+    constexpr int GV = PPT >= 4 ? 4 : 2;        // pixels per load group
+    constexpr int NG = PPT / GV;
+    constexpr int TP = kScoreThreads * PPT;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const Problem& P = a.P;
+    const float* pl = a.coords + (size_t)cd.expert * 3 * P.N;
+    const float cX = a.centres[cd.expert * 3], cY = a.centres[cd.expert * 3 + 1], cZ = a.centres[cd.expert * 3 + 2];
+
+    float2 X[NP], Y[NP], Z[NP], A[NP], B[NP], V[NP];
+#pragma unroll
+    for (int g = 0; g < NG; ++g) {
+        const int p0 = tile * TP + g * (kScoreThreads * GV) + tid * GV;
+        float x[GV], y[GV], z[GV];
+        if (a.vec_ok && p0 + GV <= P.N) {
+            if constexpr (GV == 4) {
+                float4 vx = __ldg((const float4*)(pl + p0));
+                float4 vy = __ldg((const float4*)(pl + P.N + p0));
+                float4 vz = __ldg((const float4*)(pl + 2 * (size_t)P.N + p0));
+                x[0] = vx.x; x[1] = vx.y; x[GV - 2] = vx.z; x[GV - 1] = vx.w;
+                y[0] = vy.x; y[1] = vy.y; y[GV - 2] = vy.z; y[GV - 1] = vy.w;
+                z[0] = vz.x; z[1] = vz.y; z[GV - 2] = vz.z; z[GV - 1] = vz.w;
+            } else {
+                float2 vx = __ldg((const float2*)(pl + p0));
+                float2 vy = __ldg((const float2*)(pl + P.N + p0));
+                float2 vz = __ldg((const float2*)(pl + 2 * (size_t)P.N + p0));
+                x[0] = vx.x; x[1] = vx.y; y[0] = vy.x; y[1] = vy.y; z[0] = vz.x; z[1] = vz.y;
+            }
+        } else {
+#pragma unroll
+            for (int i = 0; i < GV; ++i) {
+                int p = min(p0 + i, P.N - 1);
+                x[i] = __ldg(pl + p); y[i] = __ldg(pl + P.N + p); z[i] = __ldg(pl + 2 * (size_t)P.N + p);
+            }
+        }
+        float aa[GV], bb[GV], vv[GV];
+#pragma unroll
+        for (int i = 0; i < GV; ++i) {
+            int p = p0 + i;
+            int py = p / P.W, px = p - py * P.W;
+            // createSampling (esac_util.h:64-66): integer pixel centre, then ppoint - pixel in float
+            aa[i] = P.ppx - (float)(px * P.sub + P.sub / 2 - P.shiftX);
+            bb[i] = P.ppy - (float)(py * P.sub + P.sub / 2 - P.shiftY);
+            vv[i] = (p < P.N) ? 1.f : 0.f;
+            x[i] -= cX; y[i] -= cY; z[i] -= cZ;
+        }
+#pragma unroll
+        for (int i = 0; i < GV / 2; ++i) {
+            const int j = g * (GV / 2) + i;
+            X[j] = make_float2(x[2 * i], x[2 * i + 1]);
+            Y[j] = make_float2(y[2 * i], y[2 * i + 1]);
+            Z[j] = make_float2(z[2 * i], z[2 * i + 1]);
+            A[j] = make_float2(aa[2 * i], aa[2 * i + 1]);
+            B[j] = make_float2(bb[2 * i], bb[2 * i + 1]);
+            V[j] = make_float2(vv[2 * i], vv[2 * i + 1]);
+        }
+    }
+    const float2 k1 = make_float2(a.k1, a.k1), k0 = make_float2(a.k0, a.k0);
+    const float2 one = make_float2(1.f, 1.f), tiny = make_float2(1e-30f, 1e-30f);
+    const float mr = P.max_reproj;
+
+    for (int hl = 0; hl < cd.count; ++hl) {
+        const float4* q = sPose + hl * 6;
+        const float4 r0a = q[0], r0b = q[1], r1a = q[2], r1b = q[3], r2a = q[4], r2b = q[5];
+        float2 acc = make_float2(0.f, 0.f);
+#pragma unroll
+        for (int j = 0; j < NP; ++j) {
+            float2 xc = __ffma2_rn(lo2(r0a), X[j], __ffma2_rn(hi2(r0a), Y[j], __ffma2_rn(lo2(r0b), Z[j], hi2(r0b))));
+            float2 yc = __ffma2_rn(lo2(r1a), X[j], __ffma2_rn(hi2(r1a), Y[j], __ffma2_rn(lo2(r1b), Z[j], hi2(r1b))));
+            float2 zc = __ffma2_rn(lo2(r2a), X[j], __ffma2_rn(hi2(r2a), Y[j], __ffma2_rn(lo2(r2b), Z[j], hi2(r2b))));
+            float2 pu = __ffma2_rn(A[j], zc, xc);
+            float2 pv = __ffma2_rn(B[j], zc, yc);
+            float2 num = __ffma2_rn(pu, pu, __fmul2_rn(pv, pv));
+            float2 m = __ffma2_rn(__fmul2_rn(zc, zc), num, tiny);
+            float2 rs = make_float2(mufu_rsq(m.x), mufu_rsq(m.y));
+            float2 err = __fmul2_rn(num, rs);
+            err.x = fminf(err.x, mr);
+            err.y = fminf(err.y, mr);
+            float2 t = __ffma2_rn(err, k1, k0);
+            float2 ex = make_float2(mufu_ex2(t.x), mufu_ex2(t.y));
+            float2 den = __fadd2_rn(ex, one);
+            float2 w = make_float2(mufu_rcp(den.x), mufu_rcp(den.y));
+            if (TAIL) acc = __ffma2_rn(w, V[j], acc);
+            else acc = __fadd2_rn(acc, w);
+        }
+        float s = acc.x + acc.y;
+#pragma unroll
+        for (int o = 16; o; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+        if (lane == 0) sWarp[warp][hl] = s;
+    }
+    __syncthreads();
+    if (tid < cd.count) {
+        float s = 0.f;
+#pragma unroll
+        for (int w = 0; w < kScoreThreads / 32; ++w) s += sWarp[w][tid];
+        a.part[(size_t)(cd.slot0 + tid) * a.T + tile] = s;
+    }
+}
+
+template <int PPT>
+__global__ void __launch_bounds__(kScoreThreads, 2) score_kernel(const __grid_constant__ ScoreArgs a) {
+    __shared__ float4 sPose[kMaxChunk * 6];
+    __shared__ float sWarp[kScoreThreads / 32][kMaxChunk];
+    __shared__ int sItem;
+    constexpr int TP = kScoreThreads * PPT;
+    const int tid = threadIdx.x;
+    const int n_items = *a.n_chunks * a.T;
+    const bool ragged = (a.P.N % TP) != 0;
+    for (;;) {
+        if (tid == 0) sItem = atomicAdd(a.work_counter, 1);
+        __syncthreads();
+        const int item = sItem;
+        if (item >= n_items) break;
+        // tiles vary fastest so concurrently running CTAs share a chunk's poses and stream one plane
+        const int chunk = item / a.T, tile = item - chunk * a.T;
+        const ChunkDesc cd = a.chunks[chunk];
+        const float4* src = (const float4*)(a.poses + cd.slot0);
+        for (int i = tid; i < cd.count * 6; i += kScoreThreads) sPose[i] = src[i];
+        __syncthreads();
+        if (ragged && tile == a.T - 1) score_item<PPT, true>(a, cd, tile, sPose, sWarp);
+        else score_item<PPT, false>(a, cd, tile, sPose, sWarp);
+        __syncthreads();
+    }
+}
+
+int score_tile_pixels(int ppt) { return kScoreThreads * ppt; }
+
+void launch_score(const ScoreArgs& a, int ppt, int grid, cudaStream_t st) {
+    if (ppt == 8) score_kernel<8><<<grid, kScoreThreads, 0, st>>>(a);
+    else if (ppt == 4) score_kernel<4><<<grid, kScoreThreads, 0, st>>>(a);
+    else score_kernel<2><<<grid, kScoreThreads, 0, st>>>(a);
+}
+
+// ---------------------------------------------------------------------------------------------
+// select: finish scores, softMax, entropy, argmax (draw with training=false), contributing list
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(1024) select_kernel(const float* __restrict__ part, const int* __restrict__ slot_of,
+                                                      Problem P, int T, double* scores, double* probs, double* stats,
+                                                      int* winner, int* contrib, int* n_contrib) {
+    __shared__ double sred[32];
+    __shared__ int sidx[32];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nw = blockDim.x >> 5;
+    // getHypScores' final factor is a float expression: alpha / cols / rows (esac_util.h:256)
+    const float facf = P.alpha / (float)P.W / (float)P.H;
+    const double fac = (double)facf;
+    // one warp per hypothesis: fixed-order fp64 sum of the tile partials
+    for (int h = warp; h < P.M; h += nw) {
+        const float* row = part + (size_t)slot_of[h] * T;
+        double s = 0;
+        for (int t = lane; t < T; t += 32) s += (double)row[t];
+        for (int o = 16; o; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+        if (lane == 0) scores[h] = s * fac;
+    }
+    __syncthreads();
+    // max
+    double mx = -1e300;
+    for (int h = tid; h < P.M; h += blockDim.x) mx = fmax(mx, scores[h]);
+    for (int o = 16; o; o >>= 1) mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    if (lane == 0) sred[warp] = mx;
+    __syncthreads();
+    mx = sred[0];
+    for (int w = 1; w < nw; ++w) mx = fmax(mx, sred[w]);
+    __syncthreads();
+    double sum = 0;
+    for (int h = tid; h < P.M; h += blockDim.x) {
+        double e = exp(scores[h] - mx);
+        probs[h] = e;
+        sum += e;
+    }
+    for (int o = 16; o; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+    if (lane == 0) sred[warp] = sum;
+    __syncthreads();
+    sum = 0;
+    for (int w = 0; w < nw; ++w) sum += sred[w];
+    __syncthreads();
+    double ent = 0, best = -1;
+    int bi = 0x7fffffff;
+    for (int h = tid; h < P.M; h += blockDim.x) {
+        double p = probs[h] / sum;
+        probs[h] = p;
+        if (p > 0) ent -= p * log2(p);
+        if (!(p < kEps) && (p > best)) { best = p; bi = h; }  // first strict maximum: ascending h per thread
+    }
+    for (int o = 16; o; o >>= 1) {
+        ent += __shfl_xor_sync(0xffffffffu, ent, o);
+        double ob = __shfl_xor_sync(0xffffffffu, best, o);
+        int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+        if (ob > best || (ob == best && oi < bi)) { best = ob; bi = oi; }
+    }
+    if (lane == 0) { sred[warp] = best; sidx[warp] = bi; }
+    __syncthreads();
+    __shared__ double sent[32];
+    if (lane == 0) sent[warp] = ent;
+    __syncthreads();
+    if (tid == 0) {
+        double b = -1; int i = 0x7fffffff; double en = 0;
+        for (int w = 0; w < nw; ++w) {
+            en += sent[w];
+            if (sred[w] > b || (sred[w] == b && sidx[w] < i)) { b = sred[w]; i = sidx[w]; }
+        }
+        if (i == 0x7fffffff) i = 0;
+        *winner = i;
+        int nc = 0;
+        for (int h = 0; h < P.M; ++h)
+            if (!(probs[h] < kProbThresh)) contrib[nc++] = h;
+        *n_contrib = nc;
+        stats[0] = en; stats[1] = (double)i; stats[2] = (double)nc;
+    }
+}
+
+void launch_select(const float* part, const int* slot_of, const Problem& P, int T, double* scores, double* probs,
+                   double* stats, int* winner, int* contrib, int* n_contrib, cudaStream_t st) {
+    select_kernel<<<1, 1024, 0, st>>>(part, slot_of, P, T, scores, probs, stats, winner, contrib, n_contrib);
+}
+
+}  // namespace esacb200

@@ -1,0 +1,118 @@
+/* libesac_b200.so -- C ABI of the B200-native ESAC differentiable-RANSAC hot path.
+ *
+ * Drop-in boundary for the reference's `esac` Python extension
+ * (/root/reference/code/esac/esac.cpp:513-516: m.def("forward", &esac_forward), m.def("backward",
+ * &esac_backward)).  esacb200_forward / esacb200_backward take exactly the arguments of
+ * esac_forward (esac.cpp:64-77) / esac_backward (esac.cpp:213-230) with the at::Tensor arguments
+ * flattened to pointer + sizes; everything else in this header is additive (context handling,
+ * seeding, a scoring-only entry for measurement, read-back of intermediates for tests).
+ *
+ * Conventions
+ *  - plain C types only, no exceptions across the boundary; every entry returns 0 on success or a
+ *    negative esacb200_status, and esacb200_last_error(ctx) holds a message;
+ *  - `coords`, `grads`, `assign`, `out_pose`, `gt_pose` may be HOST or DEVICE pointers (detected with
+ *    cudaPointerGetAttributes); host buffers are copied on the context's stream (pinned memory gets
+ *    full PCIe speed), device buffers are used in place;
+ *  - calls are synchronous like the reference's (they return an int / a double), the work is enqueued
+ *    on the stream set with esacb200_set_stream (default: a stream owned by the context);
+ *  - there is NO CPU fallback: without a CUDA device esacb200_create fails.
+ */
+#ifndef ESAC_B200_H
+#define ESAC_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct esacb200_ctx esacb200_ctx;
+
+typedef enum {
+    ESACB200_OK = 0,
+    ESACB200_ERR_CUDA = -1,       /* a CUDA runtime call failed */
+    ESACB200_ERR_ARG = -2,        /* bad size / null pointer / expert index out of range */
+    ESACB200_ERR_NO_DEVICE = -3   /* no usable CUDA device */
+} esacb200_status;
+
+/* ---- context -------------------------------------------------------------------------------- */
+/* Replaces the reference's only persistent state, the static per-thread RNG
+ * (thread_rand.cpp:4-5,13-30; default seeds 1305 + thread id). */
+int esacb200_create(int device, esacb200_ctx** out);
+void esacb200_destroy(esacb200_ctx* ctx);
+const char* esacb200_last_error(const esacb200_ctx* ctx);
+/* cudaStream_t to enqueue on (0 / NULL = the context's own stream). */
+int esacb200_set_stream(esacb200_ctx* ctx, void* cuda_stream);
+/* Seed of the minimal-set stream; also resets the call counter (each forward/backward call advances
+ * it so successive calls draw fresh samples, as the reference's persistent generators do). */
+int esacb200_set_seed(esacb200_ctx* ctx, uint64_t seed);
+/* Options: "max_tries" (esac.cpp:44 MAX_SAMPLING_TRIES, default 1000000), "max_ref_steps"
+ * (esac.cpp:45 MAX_REF_STEPS, default 100), "fixed_seed" (1: do not advance the call counter),
+ * "refine_group" (CTAs per refinement job, 0 = automatic). */
+int esacb200_set_option(esacb200_ctx* ctx, const char* key, double value);
+/* Inject minimal sets instead of drawing them: cells int32 [M][T][4][2] (x, y), host pointer,
+ * copied; T candidate sets per hypothesis tried in order.  NULL clears.  Applies to the next call. */
+int esacb200_inject_cells(esacb200_ctx* ctx, const int32_t* cells, int M, int T);
+
+/* ---- the reference's two entry points ------------------------------------------------------- */
+/* esac_forward (esac.cpp:64-190).  coords float32 [E,3,H,W] contiguous; assign int64 [M] with element
+ * stride `assign_stride` (0 for the reference's expert.expand() tensors, test_esac.py:173); out_pose
+ * float32 [4,4] camera->world, written in place; *out_expert = winning expert index (the reference's
+ * return value). */
+int esacb200_forward(esacb200_ctx* ctx, const float* coords, int E, int H, int W, const int64_t* assign,
+                     int64_t assign_stride, int M, float* out_pose, int shiftX, int shiftY, float focalLength,
+                     float ppointX, float ppointY, float inlierThreshold, float inlierAlpha, float inlierBeta,
+                     float maxReproj, int subSampling, int* out_expert);
+
+/* esac_backward (esac.cpp:213-511).  grads float32 [E,3,H,W] is ACCUMULATED in place (+=, esac.cpp:501-506);
+ * gt_pose float32 [4,4] camera->world; *out_loss = expected pose loss (the reference's return value). */
+int esacb200_backward(esacb200_ctx* ctx, const float* coords, float* grads, int E, int H, int W,
+                      const int64_t* assign, int64_t assign_stride, int M, const float* gt_pose, float wLossRot,
+                      float wLossTrans, float lossCut, int shiftX, int shiftY, float focalLength, float ppointX,
+                      float ppointY, float inlierThreshold, float inlierAlpha, float inlierBeta, float maxReproj,
+                      int subSampling, double* out_loss);
+
+/* ---- additive entry points ------------------------------------------------------------------ */
+/* Soft-inlier scores of given poses (getReproErrs + getHypScores, esac_util.h:235-363) without
+ * sampling/selection/refinement: poses6 = host double [M][6] (rvec, tvec); out_scores host double [M]. */
+int esacb200_score_poses(esacb200_ctx* ctx, const float* coords, int E, int H, int W, const int64_t* assign,
+                         int64_t assign_stride, int M, const double* poses6, int shiftX, int shiftY,
+                         float focalLength, float ppointX, float ppointY, float inlierThreshold, float inlierAlpha,
+                         float inlierBeta, float maxReproj, int subSampling, double* out_scores);
+
+/* Refine given poses (refineHyp, esac_util.h:378-454): poses6 in/out host double [M][6]; out_rounds
+ * host int [M] accepted rounds; out_inliers host int [M] size of the final inlier set (may be NULL). */
+int esacb200_refine_poses(esacb200_ctx* ctx, const float* coords, int E, int H, int W, const int64_t* assign,
+                          int64_t assign_stride, int M, double* poses6, int shiftX, int shiftY, float focalLength,
+                          float ppointX, float ppointY, float inlierThreshold, float maxReproj, int subSampling,
+                          int* out_rounds, int* out_inliers);
+
+typedef struct {
+    int M;
+    int winner;            /* hypothesis index selected by draw() */
+    int n_contrib;         /* hypotheses with p >= PROB_THRESH */
+    int refine_rounds;     /* accepted refinement rounds of the winner (forward) */
+    double entropy;        /* esac_util.h:489-497 */
+    double expected_loss;  /* backward only */
+    /* device time of the last call's stages in milliseconds (CUDA events on the launching stream) */
+    float ms_h2d, ms_prep, ms_sample, ms_score, ms_select, ms_refine, ms_backward, ms_total;
+    int score_launches;    /* launches of the scoring kernel in the last call */
+    int kernel_launches;   /* all kernel launches of the last call */
+    int score_ppt, score_grid, refine_group;
+} esacb200_stats;
+int esacb200_get_stats(esacb200_ctx* ctx, esacb200_stats* out);
+
+/* Read back intermediates of the last forward/backward call (any pointer may be NULL):
+ * poses6 double [M][6] initial hypotheses, cells int32 [M][4][2], tries int32 [M], scores / probs double [M],
+ * refined6 double [M][6] (backward: refined poses; forward: only the winner's row is meaningful),
+ * losses double [M] (backward). */
+int esacb200_get_hypotheses(esacb200_ctx* ctx, double* poses6, int32_t* cells, int32_t* tries, double* scores,
+                            double* probs, double* refined6, double* losses);
+
+/* Device properties the bench needs without importing a CUDA binding: SM count and name. */
+int esacb200_device_info(esacb200_ctx* ctx, int* sm_count, char* name, int name_len);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ESAC_B200_H */
