@@ -64,6 +64,8 @@ def load_library() -> C.CDLL:
     lib.esacb200_get_stats.argtypes = [vp, C.POINTER(Stats)]
     lib.esacb200_get_hypotheses.argtypes = [vp, vp, vp, vp, vp, vp, vp, vp]
     lib.esacb200_device_info.argtypes = [vp, C.POINTER(i32), C.c_char_p, i32]
+    lib.esacb200_copy_last_scores.argtypes = [vp, vp, i32]
+    lib.esacb200_copy_last_scores.restype = i32
     for name in ("set_stream", "set_seed", "set_option", "inject_cells", "forward", "backward", "score_poses",
                  "refine_poses", "get_stats", "get_hypotheses", "device_info"):
         getattr(lib, "esacb200_" + name).restype = i32
@@ -148,6 +150,12 @@ class Context:
         s = Stats()
         self.check(self.lib.esacb200_get_stats(self.handle, C.byref(s)))
         return s.as_dict()
+
+    def copy_last_scores(self, dst):
+        """dst: float64 torch tensor (CUDA or CPU) or numpy array of M elements; stream-ordered copy."""
+        n = int(dst.numel()) if _is_torch(dst) else int(np.asarray(dst).size)
+        ptr = dst.data_ptr() if _is_torch(dst) else np.asarray(dst).ctypes.data
+        self.check(self.lib.esacb200_copy_last_scores(self.handle, ptr, n))
 
     def device_info(self) -> dict:
         n = C.c_int()

@@ -646,6 +646,15 @@ int esacb200_backward(esacb200_ctx* ctx, const float* coords, float* grads, int 
     return ESACB200_OK;
 }
 
+int esacb200_copy_last_scores(esacb200_ctx* ctx, double* dst, int M) {
+    if (!ctx || !dst) return ESACB200_ERR_ARG;
+    if (M != ctx->last_M) return fail(ctx, ESACB200_ERR_ARG, "last call had M=%d, asked for %d", ctx->last_M, M);
+    cudaSetDevice(ctx->device);
+    CK(cudaMemcpyAsync(dst, ctx->scores.p, (size_t)M * 8, cudaMemcpyDefault, ctx->stream));
+    if (!is_device_ptr(dst)) CK(cudaStreamSynchronize(ctx->stream));
+    return ESACB200_OK;
+}
+
 int esacb200_get_stats(esacb200_ctx* ctx, esacb200_stats* out) {
     if (!ctx || !out) return ESACB200_ERR_ARG;
     *out = ctx->st;

@@ -1,0 +1,78 @@
+"""Multi-GPU esac.forward: experts sharded expert-major across ranks, ONE all-gather of per-shard scores.
+
+Hypotheses are independent through sampling, P3P, scoring and (per shard) refinement; the only exchange in
+esac_forward is the softmax/argmax over all scores (esac.cpp:153-155).  Every rank therefore runs the complete
+local pipeline on the experts it owns -- including the refinement of its local best hypothesis, which costs no
+extra latency because the ranks run concurrently -- and a single all-gather of
+    [ local scores (M_local) | local refined pose (16) | global expert id | local winner index ]
+lets every rank pick the global winner with the reference's rule (first strict maximum, esac_util.h:519-523).
+Messages are KB-sized: the collective is latency-bound and is issued once per image.
+"""
+from __future__ import annotations
+
+import numpy as np
+
+
+def pack_local(scores, pose16, expert_global: int, local_winner: int):
+    """float64 vector [M_local + 18]."""
+    import torch
+    M = scores.shape[0]
+    buf = torch.empty(M + 18, dtype=torch.float64, device=scores.device)
+    buf[:M] = scores
+    buf[M:M + 16] = pose16.reshape(16).to(torch.float64)
+    buf[M + 16] = float(expert_global)
+    buf[M + 17] = float(local_winner)
+    return buf
+
+
+def select_global(gathered: np.ndarray, M_local: int):
+    """gathered: [world, M_local + 18].  Returns (global winner index, owning rank, pose 4x4 float32, expert id,
+    probabilities of all hypotheses) with softMax / draw(training=false) semantics (esac_util.h:461-530)."""
+    world = gathered.shape[0]
+    scores = gathered[:, :M_local].reshape(-1)
+    sf = np.exp(scores - scores.max())
+    probs = sf / sf.sum()
+    winner = 0
+    best = -1.0
+    for i, p in enumerate(probs):          # first strict maximum among p >= EPS
+        if p < 1e-8:
+            continue
+        if best < 0 or p > best:
+            best, winner = p, i
+    rank = winner // M_local
+    assert rank < world
+    pose = gathered[rank, M_local:M_local + 16].reshape(4, 4).astype(np.float32)
+    expert = int(gathered[rank, M_local + 16])
+    return winner, rank, pose, expert, probs
+
+
+def forward_sharded(coords_local, assign_local, out_pose, params, expert_offset: int, group=None, local_forward=None):
+    """esac.forward over experts sharded across the ranks of `group`.  coords_local [E_local,3,H,W] and
+    assign_local [M_local] (expert indices local to the shard) live on this rank; out_pose [4,4] receives the
+    global winner's camera pose on every rank; returns the global expert index."""
+    import torch
+    import torch.distributed as dist
+    from . import api
+
+    M = int(assign_local.shape[0])
+    if local_forward is None:
+        dev = coords_local.device if coords_local.is_cuda else torch.device("cuda", torch.cuda.current_device())
+        pose = torch.zeros(4, 4, device=dev)
+        e_local = api.forward(coords_local, assign_local, pose, *params)
+        ctx = api.context(dev.index)
+        scores = torch.empty(M, dtype=torch.float64, device=dev)
+        ctx.copy_last_scores(scores)
+        st = ctx.stats()
+        buf = pack_local(scores, pose, expert_offset + e_local, st["winner"])
+    else:
+        scores, pose, e_local, lw = local_forward(coords_local, assign_local, params)
+        buf = pack_local(scores, pose, expert_offset + e_local, lw)
+    world = dist.get_world_size(group)
+    gathered = torch.empty(world * (M + 18), dtype=torch.float64, device=buf.device)
+    dist.all_gather_into_tensor(gathered, buf, group=group)
+    _, _, gpose, expert, _ = select_global(gathered.view(world, M + 18).cpu().numpy(), M)
+    if hasattr(out_pose, "copy_"):
+        out_pose.copy_(torch.from_numpy(gpose))
+    else:
+        out_pose[:, :] = gpose
+    return expert

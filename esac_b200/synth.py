@@ -116,5 +116,7 @@ def pose_error(T_est: np.ndarray, T_gt: np.ndarray) -> tuple[float, float]:
     T_est = np.asarray(T_est, np.float64)
     T_gt = np.asarray(T_gt, np.float64)
     Rd = T_gt[:3, :3] @ T_est[:3, :3].T
-    c = np.clip((np.trace(Rd) - 1) / 2, -1, 1)
-    return float(np.degrees(np.arccos(c))), float(np.linalg.norm(T_est[:3, 3] - T_gt[:3, 3]))
+    # atan2 form: arccos(trace) alone cannot resolve angles below ~0.03 deg on float32 matrices
+    sin = 0.5 * np.linalg.norm([Rd[2, 1] - Rd[1, 2], Rd[0, 2] - Rd[2, 0], Rd[1, 0] - Rd[0, 1]])
+    cos = (np.trace(Rd) - 1) / 2
+    return float(np.degrees(np.arctan2(sin, cos))), float(np.linalg.norm(T_est[:3, 3] - T_gt[:3, 3]))

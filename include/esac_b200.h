@@ -109,6 +109,10 @@ int esacb200_get_stats(esacb200_ctx* ctx, esacb200_stats* out);
 int esacb200_get_hypotheses(esacb200_ctx* ctx, double* poses6, int32_t* cells, int32_t* tries, double* scores,
                             double* probs, double* refined6, double* losses);
 
+/* Copies the last call's scores (double [M]) to `dst` (host or device pointer), stream-ordered on the
+ * context's stream; used by the multi-GPU path to feed its all-gather without a host round trip. */
+int esacb200_copy_last_scores(esacb200_ctx* ctx, double* dst, int M);
+
 /* Device properties the bench needs without importing a CUDA binding: SM count and name. */
 int esacb200_device_info(esacb200_ctx* ctx, int* sm_count, char* name, int name_len);
 

@@ -103,6 +103,12 @@ def test_forward_matches_oracle(api, seed, E, H, W, M, sub, kw):
         assert st["refine_rounds"] == tr.rounds
         rot, trans = pose_error(out, ref_pose)
         assert rot < ROT_TOL_DEG and trans < TRANS_TOL_M, (rot, trans)
+        # the same comparison before the float32 rounding of outPose
+        ref6 = hy["refined"][tr.winner]
+        Ta = O.pose2trans(tr.ref_rvec, tr.ref_tvec)
+        Tb = O.pose2trans(ref6[:3].reshape(3, 1), ref6[3:].reshape(3, 1))
+        rot, trans = pose_error(Tb, Ta)
+        assert rot < ROT_TOL_DEG and trans < TRANS_TOL_M, (rot, trans)
     assert abs(st["entropy"] - tr.entropy) < 1e-3
 
 

@@ -1,0 +1,72 @@
+"""Host logic of the multi-GPU forward (esac_b200/sharded.py) on CPU: world_size-2 gloo, fake local pipelines."""
+import os
+import socket
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from esac_b200 import sharded
+
+
+def test_select_global_is_first_strict_maximum():
+    M = 5
+    g = np.zeros((3, M + 18))
+    g[0, :M] = [1, 2, 3, 2, 1]
+    g[1, :M] = [3, 9, 9, 0, 0]       # tie inside rank 1: the first one wins
+    g[2, :M] = [9, 0, 0, 0, 0]       # tie across ranks: the lower global index wins
+    for r in range(3):
+        g[r, M:M + 16] = np.eye(4).reshape(-1) * (r + 1)
+        g[r, M + 16] = 10 + r
+    w, rank, pose, expert, probs = sharded.select_global(g, M)
+    assert (w, rank, expert) == (6, 1, 11)
+    assert pose[0, 0] == 2.0 and abs(probs.sum() - 1) < 1e-12
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _worker(rank, world, port, q):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    M = 6
+    rng = np.random.default_rng(rank)
+    scores = torch.from_numpy(rng.uniform(0, 50, M))
+    if rank == 1:
+        scores[4] = 77.0  # the global winner lives on rank 1
+
+    def fake_local(coords, assign, params):
+        lw = int(torch.argmax(scores))
+        pose = torch.eye(4) * (rank + 1)
+        return scores, pose, 2, lw  # local expert id 2
+
+    out = torch.zeros(4, 4)
+    e = sharded.forward_sharded(torch.zeros(3, 3, 2, 2), torch.zeros(M, dtype=torch.int64), out, (), expert_offset=rank * 3,
+                                local_forward=fake_local)
+    q.put((rank, e, out.numpy().copy().tolist()))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_forward_sharded_world2_gloo():
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    ps = [ctx.Process(target=_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in ps:
+        p.start()
+    for p in ps:
+        p.join(timeout=240)
+        assert p.exitcode == 0
+    res = [q.get(timeout=5) for _ in range(2)]
+    for rank, e, pose in res:
+        assert e == 1 * 3 + 2          # rank 1's shard, local expert 2
+        assert np.allclose(pose, np.eye(4) * 2)
