@@ -1,0 +1,98 @@
+"""The oracle itself (CPU): known answers, internal consistency, and the C restatement against the cv2 one.
+
+The reference ships no golden vectors, so the oracle is pinned by (i) executing real
+OpenCV for every primitive, (ii) exact recovery of a known pose, (iii) agreement of two independent
+restatements (Python/cv2 and C without OpenCV) of the scoring stage, (iv) committed golden fixtures generated
+by the oracle (tests/golden/) that guard against silent drift."""
+from pathlib import Path
+
+import numpy as np
+import pytest
+
+from esac_b200.synth import make_scene, pose_error
+from oracle import esac_oracle as O
+from oracle.build import c_score
+
+GOLD = Path(__file__).resolve().parent / "golden"
+
+
+def test_forward_recovers_known_pose_noise_free():
+    sc = make_scene(E=1, H=24, W=32, M=8, sub=8, seed=2, outlier_frac=0.0, noise=0.0)
+    out = np.zeros((4, 4), np.float32)
+    e, tr = O.forward(sc.coords, sc.assign, out, *sc.params, seed=3, trace=True)
+    rot, trans = pose_error(out, sc.gt_pose)
+    assert e == 0 and rot < 1e-3 and trans < 1e-4
+    assert tr.scores[tr.winner] > 90  # nearly every cell is an inlier (alpha = 100)
+
+
+def test_forward_with_outliers_picks_gt_expert():
+    sc = make_scene(E=3, H=24, W=32, M=24, sub=8, seed=5)
+    out = np.zeros((4, 4), np.float32)
+    e = O.forward(sc.coords, sc.assign, out, *sc.params, seed=1)
+    rot, trans = pose_error(out, sc.gt_pose)
+    assert e == sc.gt_expert and rot < 1.0 and trans < 0.05
+
+
+def test_sampling_never_uses_last_row_or_column():
+    """irand(0, imW-1) -> uniform_int(0, imW-2): esac_util.h:167-168 + thread_rand.cpp:68-71."""
+    W, H = 7, 5
+    xs, ys = set(), set()
+    for h in range(20):
+        for t in range(20):
+            for (x, y) in O.draw_minimal_set(9, h, t, W, H):
+                xs.add(x); ys.add(y)
+    assert max(xs) == W - 2 and max(ys) == H - 2 and min(xs) == 0 and min(ys) == 0
+
+
+@pytest.mark.parametrize("kw", [{}, {"shiftX": 3, "shiftY": -2}, {"world_offset": 500.0}])
+def test_c_restatement_matches_cv2_oracle_scores(kw):
+    sc = make_scene(E=2, H=24, W=31, M=12, sub=8, seed=7, **kw)
+    K = O.cam_mat(sc.f, sc.ppx, sc.ppy)
+    samp = O.create_sampling(31, 24, sc.sub, sc.shiftX, sc.shiftY)
+    hyps = O.sample_hypotheses(sc.coords, sc.assign, samp, K, 10000, sc.tau, 5)
+    errs = [O.get_repro_errs(sc.coords, h.rvec, h.tvec, int(sc.assign[i]), samp, K, sc.max_reproj)[0] for i, h in enumerate(hyps)]
+    ref = np.array(O.get_hyp_scores(errs, sc.tau, sc.alpha, sc.beta))
+    p6 = np.array([np.concatenate([h.rvec.ravel(), h.tvec.ravel()]) for h in hyps])
+    got, _ = c_score(sc.coords, sc.assign, p6, *sc.params)
+    assert np.abs(got - ref).max() < 1e-10
+
+
+def test_softmax_entropy_draw():
+    p = O.softmax([1.0, 3.0, 3.0, 2.0])
+    assert abs(p.sum() - 1) < 1e-15 and O.draw(p) == 1  # first strict maximum
+    assert abs(O.entropy([0.5, 0.5]) - 1.0) < 1e-15
+    assert O.entropy([1.0, 0.0]) == 0.0
+
+
+def test_loss_cut_and_clamp():
+    T = np.eye(4)
+    T2 = np.eye(4); T2[:3, 3] = [3.0, 0, 0]
+    assert abs(O.loss(T, T2, 1.0, 100.0, 1e9) - 300.0) < 1e-9
+    assert abs(O.loss(T, T2, 1.0, 100.0, 100.0) - np.sqrt(100.0 * 300.0)) < 1e-9
+
+
+def test_backward_accumulates_and_only_touches_assigned_experts():
+    sc = make_scene(E=3, H=16, W=20, M=12, sub=8, seed=11)
+    g = np.full_like(sc.coords, 0.25)
+    loss, bt = O.backward(sc.coords, g, sc.assign, sc.gt_pose, 1.0, 100.0, 100.0, *sc.params, seed=2, trace=True)
+    assert loss > 0 and np.isfinite(g).all()
+    used = set(int(sc.assign[h]) for h in range(len(sc.assign)) if bt.probs[h] >= O.PROB_THRESH)
+    for e in range(3):
+        if e not in used:
+            assert np.all(g[e] == 0.25)
+    assert any(np.any(g[e] != 0.25) for e in used)
+
+
+def test_golden_fixtures_still_reproduce():
+    """tests/golden/*.npz were written by tests/golden/make_golden.py from this oracle."""
+    files = sorted(GOLD.glob("*.npz"))
+    assert files, "run python tests/golden/make_golden.py"
+    for f in files:
+        z = np.load(f)
+        out = np.zeros((4, 4), np.float32)
+        params = tuple(z["params"].tolist())
+        params = (int(params[0]), int(params[1])) + tuple(float(v) for v in params[2:9]) + (int(params[9]),)
+        e, tr = O.forward(z["coords"], z["assign"], out, *params, seed=int(z["seed"]), trace=True)
+        assert e == int(z["expert"])
+        assert np.abs(np.array(tr.scores) - z["scores"]).max() < 1e-9
+        assert np.abs(out - z["pose"]).max() < 1e-6
