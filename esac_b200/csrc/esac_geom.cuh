@@ -199,14 +199,38 @@ ESAC_HD void d_project_d_obj(float ptx_f, float pty_f, float Xf, float Yf, float
 }
 
 // ---------------------------------------------------------------------------------------------
-// small dense algebra
+// small dense algebra (templated: the P3P core also runs in float as a rejection prefilter)
 // ---------------------------------------------------------------------------------------------
-ESAC_HD double det3(const double A[9]) {
+template <typename T> struct Num;
+template <> struct Num<double> {
+    static ESAC_HD double sqrt_(double v) { return sqrt(v); }
+    static ESAC_HD double acos_(double v) { return acos(v); }
+    static ESAC_HD double cos_(double v) { return cos(v); }
+    static ESAC_HD double cbrt_(double v) { return cbrt(v); }
+    static ESAC_HD double abs_(double v) { return fabs(v); }
+    static constexpr double kRelTiny = 1e-14;   // "this coefficient is zero" threshold
+    static constexpr double kDiscTol = 1e-13;   // slightly negative discriminants are clamped to 0
+    static constexpr double kUncertain = 0.0;   // no uncertainty band in double
+};
+template <> struct Num<float> {
+    static ESAC_HD float sqrt_(float v) { return sqrtf(v); }
+    static ESAC_HD float acos_(float v) { return acosf(v); }
+    static ESAC_HD float cos_(float v) { return cosf(v); }
+    static ESAC_HD float cbrt_(float v) { return cbrtf(v); }
+    static ESAC_HD float abs_(float v) { return fabsf(v); }
+    static constexpr float kRelTiny = 1e-6f;
+    static constexpr float kDiscTol = 1e-5f;
+    static constexpr float kUncertain = 2e-3f;  // sign decisions closer to zero than this (relative) are "uncertain"
+};
+
+template <typename T>
+ESAC_HD T det3(const T A[9]) {
     return A[0] * (A[4] * A[8] - A[5] * A[7]) - A[1] * (A[3] * A[8] - A[5] * A[6]) + A[2] * (A[3] * A[7] - A[4] * A[6]);
 }
 
 // adjugate (transpose of the cofactor matrix) of a 3x3
-ESAC_HD void adj3(const double A[9], double B[9]) {
+template <typename T>
+ESAC_HD void adj3(const T A[9], T B[9]) {
     B[0] = A[4] * A[8] - A[5] * A[7];
     B[1] = A[2] * A[7] - A[1] * A[8];
     B[2] = A[1] * A[5] - A[2] * A[4];
@@ -218,7 +242,8 @@ ESAC_HD void adj3(const double A[9], double B[9]) {
     B[8] = A[0] * A[4] - A[1] * A[3];
 }
 
-ESAC_HD double trace_prod3(const double A[9], const double B[9]) {  // tr(A*B)
+template <typename T>
+ESAC_HD T trace_prod3(const T A[9], const T B[9]) {  // tr(A*B)
     return A[0] * B[0] + A[1] * B[3] + A[2] * B[6] + A[3] * B[1] + A[4] * B[4] + A[5] * B[7] + A[6] * B[2] +
            A[7] * B[5] + A[8] * B[8];
 }
@@ -322,54 +347,58 @@ ESAC_HDN void pinv_sym6(const double Ain[36], double out[36]) {
 // lam[i] > 0 with |lam_i y_i - lam_j y_j|^2 = |x_i - x_j|^2.  The two homogeneous conics
 //     D1 = a23*Q12 - a12*Q23,   D2 = a23*Q13 - a13*Q23
 // share the solutions; a degenerate member D1 + g*D2 of their pencil (cubic in g) splits into two
-// lines, each line meets a conic in <= 2 points -> <= 4 depth triples, polished by Gauss-Newton on
-// the three distance equations, then turned into (R, t) by aligning the two congruent triangles.
-// Returns the number of solutions (0..4); Rs row-major.
+// lines, each line meets a conic in <= 2 points -> <= 4 depth triples (p3p_lambdas, float or double),
+// polished by Gauss-Newton on the three distance equations, then turned into (R, t) by aligning the two
+// congruent triangles (p3p_solve, double).
 // ---------------------------------------------------------------------------------------------
-ESAC_HD double quad3(const double D[9], const double a[3], const double b[3]) {  // a^T D b
+template <typename T>
+ESAC_HD T quad3(const T D[9], const T a[3], const T b[3]) {  // a^T D b
     return a[0] * (D[0] * b[0] + D[1] * b[1] + D[2] * b[2]) + a[1] * (D[3] * b[0] + D[4] * b[1] + D[5] * b[2]) +
            a[2] * (D[6] * b[0] + D[7] * b[1] + D[8] * b[2]);
 }
 
-ESAC_HD int real_cubic_roots(double c3, double c2, double c1, double c0, double roots[3]) {
+template <typename T>
+ESAC_HD int real_cubic_roots(T c3, T c2, T c1, T c0, T roots[3]) {
+    using N = Num<T>;
     int n = 0;
-    double scale = fabs(c3) + fabs(c2) + fabs(c1) + fabs(c0);
+    T scale = N::abs_(c3) + N::abs_(c2) + N::abs_(c1) + N::abs_(c0);
     if (!(scale > 0)) return 0;
-    if (fabs(c3) < 1e-14 * scale) {  // quadratic (the root at infinity is handled by the caller)
-        if (fabs(c2) < 1e-14 * scale) {
-            if (fabs(c1) > 0) roots[n++] = -c0 / c1;
+    if (N::abs_(c3) < N::kRelTiny * scale) {  // quadratic (the root at infinity is handled by the caller)
+        if (N::abs_(c2) < N::kRelTiny * scale) {
+            if (N::abs_(c1) > 0) roots[n++] = -c0 / c1;
             return n;
         }
-        double disc = c1 * c1 - 4 * c2 * c0;
+        T disc = c1 * c1 - 4 * c2 * c0;
         if (disc < 0) return 0;
-        double sq = sqrt(disc);
-        double q = -0.5 * (c1 + (c1 >= 0 ? sq : -sq));
+        T sq = N::sqrt_(disc);
+        T q = T(-0.5) * (c1 + (c1 >= 0 ? sq : -sq));
         roots[n++] = q / c2;
         if (q != 0) roots[n++] = c0 / q;
         return n;
     }
-    double a = c2 / c3, b = c1 / c3, c = c0 / c3;
-    double Q = (a * a - 3 * b) / 9, Rr = (2 * a * a * a - 9 * a * b + 27 * c) / 54;
-    double Q3 = Q * Q * Q;
+    T a = c2 / c3, b = c1 / c3, c = c0 / c3;
+    T Q = (a * a - 3 * b) / 9, Rr = (2 * a * a * a - 9 * a * b + 27 * c) / 54;
+    T Q3 = Q * Q * Q;
     if (Rr * Rr < Q3) {
-        double th = acos(Rr / sqrt(Q3));
-        double sq = -2 * sqrt(Q);
-        roots[0] = sq * cos(th / 3) - a / 3;
-        roots[1] = sq * cos((th + 2 * kPi) / 3) - a / 3;
-        roots[2] = sq * cos((th - 2 * kPi) / 3) - a / 3;
+        T th = N::acos_(Rr / N::sqrt_(Q3));
+        T sq = -2 * N::sqrt_(Q);
+        const T twopi = T(2 * 3.14159265358979323846);
+        roots[0] = sq * N::cos_(th / 3) - a / 3;
+        roots[1] = sq * N::cos_((th + twopi) / 3) - a / 3;
+        roots[2] = sq * N::cos_((th - twopi) / 3) - a / 3;
         n = 3;
     } else {
-        double A = -(Rr >= 0 ? 1. : -1.) * cbrt(fabs(Rr) + sqrt(Rr * Rr - Q3));
-        double B = A != 0 ? Q / A : 0;
+        T A = -(Rr >= 0 ? T(1) : T(-1)) * N::cbrt_(N::abs_(Rr) + N::sqrt_(Rr * Rr - Q3));
+        T B = A != 0 ? Q / A : 0;
         roots[0] = A + B - a / 3;
         n = 1;
     }
     for (int i = 0; i < n; ++i) {  // Newton polish on the monic cubic
-        double g = roots[i];
+        T g = roots[i];
         for (int it = 0; it < 4; ++it) {
-            double fv = ((g + a) * g + b) * g + c;
-            double dv = (3 * g + 2 * a) * g + b;
-            if (!(fabs(dv) > 0)) break;
+            T fv = ((g + a) * g + b) * g + c;
+            T dv = (3 * g + 2 * a) * g + b;
+            if (!(N::abs_(dv) > 0)) break;
             g -= fv / dv;
         }
         roots[i] = g;
@@ -378,36 +407,37 @@ ESAC_HD int real_cubic_roots(double c3, double c2, double c1, double c0, double 
 }
 
 // Intersect the line {lam : l.lam = 0} with the conic lam^T D lam = 0; appends direction vectors.
-ESAC_HD int line_conic(const double l[3], const double D[9], double sol[][3], int n) {
+template <typename T>
+ESAC_HD int line_conic(const T l[3], const T D[9], T sol[][3], int n, bool& uncertain) {
+    using N = Num<T>;
     int k = 0;
-    if (fabs(l[1]) > fabs(l[k])) k = 1;
-    if (fabs(l[2]) > fabs(l[k])) k = 2;
-    if (!(fabs(l[k]) > 0)) return n;
+    if (N::abs_(l[1]) > N::abs_(l[k])) k = 1;
+    if (N::abs_(l[2]) > N::abs_(l[k])) k = 2;
+    if (!(N::abs_(l[k]) > 0)) return n;
     int i = (k + 1) % 3, j = (k + 2) % 3;
-    double u[3] = {0, 0, 0}, v[3] = {0, 0, 0};
+    T u[3] = {0, 0, 0}, v[3] = {0, 0, 0};
     u[i] = 1; u[k] = -l[i] / l[k];
     v[j] = 1; v[k] = -l[j] / l[k];
-    double A = quad3(D, u, u), B = quad3(D, u, v), C = quad3(D, v, v);
-    double disc = B * B - A * C;
-    double tol = 1e-13 * (B * B + fabs(A * C));
-    if (disc < -tol) return n;
+    T A = quad3(D, u, u), B = quad3(D, u, v), C = quad3(D, v, v);
+    T disc = B * B - A * C;
+    T mag = B * B + N::abs_(A * C);
+    if (N::abs_(disc) < N::kUncertain * mag) uncertain = true;
+    if (disc < -N::kDiscTol * mag) return n;
     if (disc < 0) disc = 0;
-    double sq = sqrt(disc);
-    if (fabs(A) >= fabs(C)) {
-        if (!(fabs(A) > 0)) return n;
-        // alpha = (-B +- sq)/A, beta = 1 (stable form)
-        double q = -(B + (B >= 0 ? sq : -sq));
-        double a1 = q / A, a2 = (q != 0) ? C / q : a1;
+    T sq = N::sqrt_(disc);
+    T q = -(B + (B >= 0 ? sq : -sq));
+    if (N::abs_(A) >= N::abs_(C)) {
+        if (!(N::abs_(A) > 0)) return n;
+        T a1 = q / A, a2 = (q != 0) ? C / q : a1;  // alpha = (-B +- sq)/A, beta = 1 (stable form)
         for (int s = 0; s < 2; ++s) {
-            double al = s == 0 ? a1 : a2;
+            T al = s == 0 ? a1 : a2;
             for (int c = 0; c < 3; ++c) sol[n][c] = al * u[c] + v[c];
             ++n;
         }
     } else {
-        double q = -(B + (B >= 0 ? sq : -sq));
-        double b1 = q / C, b2 = (q != 0) ? A / q : b1;
+        T b1 = q / C, b2 = (q != 0) ? A / q : b1;
         for (int s = 0; s < 2; ++s) {
-            double be = s == 0 ? b1 : b2;
+            T be = s == 0 ? b1 : b2;
             for (int c = 0; c < 3; ++c) sol[n][c] = u[c] + be * v[c];
             ++n;
         }
@@ -415,25 +445,28 @@ ESAC_HD int line_conic(const double l[3], const double D[9], double sol[][3], in
     return n;
 }
 
-ESAC_HD void cross3(const double a[3], const double b[3], double c[3]) {
+template <typename T>
+ESAC_HD void cross3(const T a[3], const T b[3], T c[3]) {
     c[0] = a[1] * b[2] - a[2] * b[1];
     c[1] = a[2] * b[0] - a[0] * b[2];
     c[2] = a[0] * b[1] - a[1] * b[0];
 }
 
 // Orthonormal frame of a triangle: e1 along p0-p1, e3 along (p0-p1) x (p1-p2), e2 = e3 x e1 (columns of F).
-ESAC_HD bool tri_frame(const double p0[3], const double p1[3], const double p2[3], double F[9]) {
-    double d1[3] = {p0[0] - p1[0], p0[1] - p1[1], p0[2] - p1[2]};
-    double d2[3] = {p1[0] - p2[0], p1[1] - p2[1], p1[2] - p2[2]};
-    double n1 = sqrt(d1[0] * d1[0] + d1[1] * d1[1] + d1[2] * d1[2]);
+template <typename T>
+ESAC_HD bool tri_frame(const T p0[3], const T p1[3], const T p2[3], T F[9]) {
+    using N = Num<T>;
+    T d1[3] = {p0[0] - p1[0], p0[1] - p1[1], p0[2] - p1[2]};
+    T d2[3] = {p1[0] - p2[0], p1[1] - p2[1], p1[2] - p2[2]};
+    T n1 = N::sqrt_(d1[0] * d1[0] + d1[1] * d1[1] + d1[2] * d1[2]);
     if (!(n1 > 0)) return false;
-    double e1[3] = {d1[0] / n1, d1[1] / n1, d1[2] / n1};
-    double e3[3];
+    T e1[3] = {d1[0] / n1, d1[1] / n1, d1[2] / n1};
+    T e3[3];
     cross3(d1, d2, e3);
-    double n3 = sqrt(e3[0] * e3[0] + e3[1] * e3[1] + e3[2] * e3[2]);
+    T n3 = N::sqrt_(e3[0] * e3[0] + e3[1] * e3[1] + e3[2] * e3[2]);
     if (!(n3 > 0)) return false;
     e3[0] /= n3; e3[1] /= n3; e3[2] /= n3;
-    double e2[3];
+    T e2[3];
     cross3(e3, e1, e2);
     for (int r = 0; r < 3; ++r) {
         F[r * 3 + 0] = e1[r];
@@ -443,105 +476,157 @@ ESAC_HD bool tri_frame(const double p0[3], const double p1[3], const double p2[3
     return true;
 }
 
-ESAC_HDN int p3p_solve(const double y[3][3], const double x[3][3], double Rs[4][9], double ts[4][3]) {
-    double d12[3], d13[3], d23[3];
+// Rigid transform mapping triangle x (scene) onto triangle P (camera): R row-major, t.
+template <typename T>
+ESAC_HD bool align_triangles(const T P[3][3], const T x[3][3], T R[9], T t[3]) {
+    T Fc[9], Fw[9];
+    if (!tri_frame(P[0], P[1], P[2], Fc) || !tri_frame(x[0], x[1], x[2], Fw)) return false;
+    for (int r = 0; r < 3; ++r)
+        for (int c = 0; c < 3; ++c)
+            R[r * 3 + c] = Fc[r * 3 + 0] * Fw[c * 3 + 0] + Fc[r * 3 + 1] * Fw[c * 3 + 1] + Fc[r * 3 + 2] * Fw[c * 3 + 2];
+    T mc[3], mw[3];
+    for (int c = 0; c < 3; ++c) {
+        mc[c] = (P[0][c] + P[1][c] + P[2][c]) / 3;
+        mw[c] = (x[0][c] + x[1][c] + x[2][c]) / 3;
+    }
+    for (int r = 0; r < 3; ++r) t[r] = mc[r] - (R[r * 3] * mw[0] + R[r * 3 + 1] * mw[1] + R[r * 3 + 2] * mw[2]);
+    return true;
+}
+
+// Depth triples (unpolished), in units where the largest squared side of the scene triangle is 1.
+// cs = {c12, c13, c23} cosines between bearings, ss = {s12, s13, s23} normalised squared sides.
+// `uncertain` is raised (float only) when a sign decision was taken too close to zero to be trusted.
+template <typename T>
+ESAC_HD int p3p_lambdas(const T y[3][3], const T x[3][3], T lam[4][3], T& amax, T cs[3], T ss[3], bool& uncertain) {
+    using N = Num<T>;
+    uncertain = false;
+    T d12[3], d13[3], d23[3];
     for (int c = 0; c < 3; ++c) {
         d12[c] = x[0][c] - x[1][c];
         d13[c] = x[0][c] - x[2][c];
         d23[c] = x[1][c] - x[2][c];
     }
-    double a12 = d12[0] * d12[0] + d12[1] * d12[1] + d12[2] * d12[2];
-    double a13 = d13[0] * d13[0] + d13[1] * d13[1] + d13[2] * d13[2];
-    double a23 = d23[0] * d23[0] + d23[1] * d23[1] + d23[2] * d23[2];
-    double amax = fmax(a12, fmax(a13, a23));
-    if (!(amax > 0) || !(fmin(a12, fmin(a13, a23)) > 1e-24 * amax) || !(amax < 1e300)) return 0;
-    double c12 = y[0][0] * y[1][0] + y[0][1] * y[1][1] + y[0][2] * y[1][2];
-    double c13 = y[0][0] * y[2][0] + y[0][1] * y[2][1] + y[0][2] * y[2][2];
-    double c23 = y[1][0] * y[2][0] + y[1][1] * y[2][1] + y[1][2] * y[2][2];
-    // work with distances normalised by amax (conditioning); depths are rescaled at the end
-    double s12 = a12 / amax, s13 = a13 / amax, s23 = a23 / amax;
-    double D1[9] = {s23, -s23 * c12, 0, -s23 * c12, s23 - s12, s12 * c23, 0, s12 * c23, -s12};
-    double D2[9] = {s23, 0, -s23 * c13, 0, -s13, s13 * c23, -s23 * c13, s13 * c23, s23 - s13};
-    double B1[9], B2[9];
+    T a12 = d12[0] * d12[0] + d12[1] * d12[1] + d12[2] * d12[2];
+    T a13 = d13[0] * d13[0] + d13[1] * d13[1] + d13[2] * d13[2];
+    T a23 = d23[0] * d23[0] + d23[1] * d23[1] + d23[2] * d23[2];
+    amax = a12 > a13 ? (a12 > a23 ? a12 : a23) : (a13 > a23 ? a13 : a23);
+    T amin = a12 < a13 ? (a12 < a23 ? a12 : a23) : (a13 < a23 ? a13 : a23);
+    if (!(amax > 0) || !(amin > T(1e-24) * amax) || !(amax < T(1e30))) return 0;
+    T c12 = y[0][0] * y[1][0] + y[0][1] * y[1][1] + y[0][2] * y[1][2];
+    T c13 = y[0][0] * y[2][0] + y[0][1] * y[2][1] + y[0][2] * y[2][2];
+    T c23 = y[1][0] * y[2][0] + y[1][1] * y[2][1] + y[1][2] * y[2][2];
+    T s12 = a12 / amax, s13 = a13 / amax, s23 = a23 / amax;
+    if (N::kUncertain > 0) {  // float prefilter: needle triangles / nearly parallel bearings are left to the exact path
+        const T cm = N::abs_(c12) > N::abs_(c13) ? (N::abs_(c12) > N::abs_(c23) ? N::abs_(c12) : N::abs_(c23))
+                                                 : (N::abs_(c13) > N::abs_(c23) ? N::abs_(c13) : N::abs_(c23));
+        if (amin < T(0.02) * amax || cm > T(0.9999)) uncertain = true;
+    }
+    cs[0] = c12; cs[1] = c13; cs[2] = c23;
+    ss[0] = s12; ss[1] = s13; ss[2] = s23;
+    T D1[9] = {s23, -s23 * c12, 0, -s23 * c12, s23 - s12, s12 * c23, 0, s12 * c23, -s12};
+    T D2[9] = {s23, 0, -s23 * c13, 0, -s13, s13 * c23, -s23 * c13, s13 * c23, s23 - s13};
+    T B1[9], B2[9];
     adj3(D1, B1);
     adj3(D2, B2);
-    double k0 = det3(D1), k1 = trace_prod3(B1, D2), k2 = trace_prod3(D1, B2), k3 = det3(D2);
-    double roots[4];
+    T k0 = det3(D1), k1 = trace_prod3(B1, D2), k2 = trace_prod3(D1, B2), k3 = det3(D2);
+    T roots[4];
     int nr = real_cubic_roots(k3, k2, k1, k0, roots);
-    double kscale = fabs(k3) + fabs(k2) + fabs(k1) + fabs(k0);
-    bool inf_root = fabs(k3) < 1e-14 * kscale;
-    double dirs[8][3];
+    T kscale = N::abs_(k3) + N::abs_(k2) + N::abs_(k1) + N::abs_(k0);
+    bool inf_root = N::abs_(k3) < N::kRelTiny * kscale;
+    T dirs[8][3];
     int nd = 0;
     for (int ri = 0; ri < nr + (inf_root ? 1 : 0) && nd == 0; ++ri) {
-        double D0[9];
-        const double* Dother;
+        T D0[9];
+        const T* Dother;
         if (ri >= nr) {  // D2 itself is the degenerate member
             for (int i = 0; i < 9; ++i) D0[i] = D2[i];
             Dother = D1;
         } else {
-            double g = roots[ri];
-            if (fabs(g) <= 1) {
+            T g = roots[ri];
+            if (N::abs_(g) <= 1) {
                 for (int i = 0; i < 9; ++i) D0[i] = D1[i] + g * D2[i];
                 Dother = D2;
             } else {
-                double ig = 1. / g;
+                T ig = 1 / g;
                 for (int i = 0; i < 9; ++i) D0[i] = ig * D1[i] + D2[i];
                 Dother = D1;
             }
         }
-        double B[9];
+        T B[9];
         adj3(D0, B);  // = -p p^T with p = l x m for a real line pair
         int i = 0;
-        if (fabs(B[4]) > fabs(B[i * 4])) i = 1;
-        if (fabs(B[8]) > fabs(B[i * 4])) i = 2;
-        double bii = B[i * 4];
+        if (N::abs_(B[4]) > N::abs_(B[i * 4])) i = 1;
+        if (N::abs_(B[8]) > N::abs_(B[i * 4])) i = 2;
+        T bii = B[i * 4];
+        T nb = 0, nD = 0;
+        for (int q = 0; q < 9; ++q) { nb += N::abs_(B[q]); nD += N::abs_(D0[q]); }
+        if (N::abs_(bii) < N::kUncertain * nD * nD) uncertain = true;
         if (!(bii < 0)) {
             // rank <= 1 (double line) or complex line pair.  A double line shows up as B == 0.
-            double nb = 0, nD = 0;
-            for (int q = 0; q < 9; ++q) { nb += fabs(B[q]); nD += fabs(D0[q]); }
-            if (nb <= 1e-14 * nD * nD) {
+            if (nb <= N::kRelTiny * nD * nD) {
                 int rr = 0;
-                for (int q = 1; q < 3; ++q) if (fabs(D0[q * 4]) > fabs(D0[rr * 4])) rr = q;
-                double l[3] = {D0[rr * 3], D0[rr * 3 + 1], D0[rr * 3 + 2]};
-                nd = line_conic(l, Dother, dirs, nd);
+                for (int q = 1; q < 3; ++q) if (N::abs_(D0[q * 4]) > N::abs_(D0[rr * 4])) rr = q;
+                T l[3] = {D0[rr * 3], D0[rr * 3 + 1], D0[rr * 3 + 2]};
+                nd = line_conic(l, Dother, dirs, nd, uncertain);
             }
             continue;
         }
-        double sq = sqrt(-bii);
-        double p[3] = {B[i] / sq, B[3 + i] / sq, B[6 + i] / sq};
-        double C[9] = {D0[0], D0[1] - p[2], D0[2] + p[1], D0[3] + p[2], D0[4], D0[5] - p[0],
-                       D0[6] - p[1], D0[7] + p[0], D0[8]};
+        T sq = N::sqrt_(-bii);
+        T p[3] = {B[i] / sq, B[3 + i] / sq, B[6 + i] / sq};
+        T C[9] = {D0[0], D0[1] - p[2], D0[2] + p[1], D0[3] + p[2], D0[4], D0[5] - p[0],
+                  D0[6] - p[1], D0[7] + p[0], D0[8]};
         int rm = 0, cm = 0;
-        double best = -1;
+        T best = -1;
         for (int r = 0; r < 3; ++r)
             for (int c = 0; c < 3; ++c)
-                if (fabs(C[r * 3 + c]) > best) { best = fabs(C[r * 3 + c]); rm = r; cm = c; }
+                if (N::abs_(C[r * 3 + c]) > best) { best = N::abs_(C[r * 3 + c]); rm = r; cm = c; }
         if (!(best > 0)) continue;
-        double l[3] = {C[rm * 3], C[rm * 3 + 1], C[rm * 3 + 2]};
-        double m[3] = {C[cm], C[3 + cm], C[6 + cm]};
-        nd = line_conic(l, Dother, dirs, nd);
-        nd = line_conic(m, Dother, dirs, nd);
+        T l[3] = {C[rm * 3], C[rm * 3 + 1], C[rm * 3 + 2]};
+        T m[3] = {C[cm], C[3 + cm], C[6 + cm]};
+        nd = line_conic(l, Dother, dirs, nd, uncertain);
+        nd = line_conic(m, Dother, dirs, nd, uncertain);
     }
     int ns = 0;
     for (int d = 0; d < nd && ns < 4; ++d) {
-        double lam[3] = {dirs[d][0], dirs[d][1], dirs[d][2]};
-        // fix the scale with the best-conditioned distance equation
-        double q12 = lam[0] * lam[0] + lam[1] * lam[1] - 2 * c12 * lam[0] * lam[1];
-        double q13 = lam[0] * lam[0] + lam[2] * lam[2] - 2 * c13 * lam[0] * lam[2];
-        double q23 = lam[1] * lam[1] + lam[2] * lam[2] - 2 * c23 * lam[1] * lam[2];
-        double sc;
-        if (q12 * s13 >= q13 * s12 && q12 * s23 >= q23 * s12) sc = s12 / q12;
-        else if (q13 * s23 >= q23 * s13) sc = s13 / q13;
+        T l0 = dirs[d][0], l1 = dirs[d][1], l2 = dirs[d][2];
+        T q12 = l0 * l0 + l1 * l1 - 2 * c12 * l0 * l1;
+        T q13 = l0 * l0 + l2 * l2 - 2 * c13 * l0 * l2;
+        T q23 = l1 * l1 + l2 * l2 - 2 * c23 * l1 * l2;
+        T sc;  // fix the scale with the largest quadratic form
+        if (q12 >= q13 && q12 >= q23) sc = s12 / q12;
+        else if (q13 >= q23) sc = s13 / q13;
         else sc = s23 / q23;
-        if (!(sc > 0) || !(sc < 1e300)) continue;
-        sc = sqrt(sc);
-        int pos = (lam[0] > 0) + (lam[1] > 0) + (lam[2] > 0);
-        int neg = (lam[0] < 0) + (lam[1] < 0) + (lam[2] < 0);
+        if (!(sc > 0) || !(sc < T(1e30))) continue;
+        sc = N::sqrt_(sc);
+        T mx = N::abs_(l0) > N::abs_(l1) ? N::abs_(l0) : N::abs_(l1);
+        mx = mx > N::abs_(l2) ? mx : N::abs_(l2);
+        if (N::abs_(l0) < N::kUncertain * mx || N::abs_(l1) < N::kUncertain * mx || N::abs_(l2) < N::kUncertain * mx) uncertain = true;
+        int pos = (l0 > 0) + (l1 > 0) + (l2 > 0);
+        int neg = (l0 < 0) + (l1 < 0) + (l2 < 0);
         if (neg == 3) sc = -sc;
         else if (pos != 3) continue;
-        for (int c = 0; c < 3; ++c) lam[c] *= sc;
+        lam[ns][0] = l0 * sc; lam[ns][1] = l1 * sc; lam[ns][2] = l2 * sc;
+        if (N::kUncertain > 0) {  // float prefilter: an inaccurate candidate (distance equations not met) is not trusted
+            const T a0 = lam[ns][0], a1 = lam[ns][1], a2 = lam[ns][2];
+            T r = N::abs_(a0 * a0 + a1 * a1 - 2 * c12 * a0 * a1 - s12) + N::abs_(a0 * a0 + a2 * a2 - 2 * c13 * a0 * a2 - s13) +
+                  N::abs_(a1 * a1 + a2 * a2 - 2 * c23 * a1 * a2 - s23);
+            if (!(r < T(1e-4) * (a0 * a0 + a1 * a1 + a2 * a2 + 1))) uncertain = true;
+        }
+        ++ns;
+    }
+    return ns;
+}
+
+// All P3P solutions (R row-major, t), polished to machine precision.  Returns the count (0..4).
+ESAC_HDN int p3p_solve(const double y[3][3], const double x[3][3], double Rs[4][9], double ts[4][3]) {
+    double lams[4][3], amax, cs[3], ss[3];
+    bool unc;
+    int nl = p3p_lambdas<double>(y, x, lams, amax, cs, ss, unc);
+    const double c12 = cs[0], c13 = cs[1], c23 = cs[2], s12 = ss[0], s13 = ss[1], s23 = ss[2];
+    int ns = 0;
+    for (int d = 0; d < nl && ns < 4; ++d) {
+        double lam[3] = {lams[d][0], lams[d][1], lams[d][2]};
         // Gauss-Newton polish on the three (normalised) distance equations
-        bool ok = true;
         double res = 0;
         for (int it = 0; it < 6; ++it) {
             double r[3] = {lam[0] * lam[0] + lam[1] * lam[1] - 2 * c12 * lam[0] * lam[1] - s12,
@@ -556,35 +641,31 @@ ESAC_HDN int p3p_solve(const double y[3][3], const double x[3][3], double Rs[4][
             if (!solve3(Jm, r, dl)) break;  // singular: keep the current estimate
             lam[0] -= dl[0]; lam[1] -= dl[1]; lam[2] -= dl[2];
         }
-        if (!(res < 1e-9) || !(lam[0] > 0 && lam[1] > 0 && lam[2] > 0)) ok = false;
-        if (!ok) continue;
-        // reject duplicates (double roots)
-        bool dup = false;
+        if (!(res < 1e-9) || !(lam[0] > 0 && lam[1] > 0 && lam[2] > 0)) continue;
         double sa = sqrt(amax);
         double P[3][3];
         for (int i = 0; i < 3; ++i)
             for (int c = 0; c < 3; ++c) P[i][c] = lam[i] * sa * y[i][c];
-        double Fc[9], Fw[9];
-        if (!tri_frame(P[0], P[1], P[2], Fc) || !tri_frame(x[0], x[1], x[2], Fw)) continue;
-        double* R = Rs[ns];
-        for (int r = 0; r < 3; ++r)
-            for (int c = 0; c < 3; ++c)
-                R[r * 3 + c] = Fc[r * 3 + 0] * Fw[c * 3 + 0] + Fc[r * 3 + 1] * Fw[c * 3 + 1] + Fc[r * 3 + 2] * Fw[c * 3 + 2];
-        double mc[3], mw[3];
-        for (int c = 0; c < 3; ++c) {
-            mc[c] = (P[0][c] + P[1][c] + P[2][c]) / 3;
-            mw[c] = (x[0][c] + x[1][c] + x[2][c]) / 3;
-        }
-        for (int r = 0; r < 3; ++r) ts[ns][r] = mc[r] - (R[r * 3] * mw[0] + R[r * 3 + 1] * mw[1] + R[r * 3 + 2] * mw[2]);
+        if (!align_triangles<double>(P, x, Rs[ns], ts[ns])) continue;
+        bool dup = false;  // reject duplicates (double roots)
         for (int q = 0; q < ns; ++q) {
             double dd = 0;
             for (int c = 0; c < 3; ++c) dd += fabs(ts[q][c] - ts[ns][c]);
-            for (int c = 0; c < 9; ++c) dd += fabs(Rs[q][c] - R[c]);
+            for (int c = 0; c < 9; ++c) dd += fabs(Rs[q][c] - Rs[ns][c]);
             if (dd < 1e-9) dup = true;
         }
         if (!dup) ++ns;
     }
     return ns;
+}
+
+// Bearing of an image point the way cv::solvePnP hands it to P3P: undistortPoints on float points gives
+// (u - cx) * (1/fx) rounded to float (a ~1e-5 px perturbation that shows up in the 4.13 oracle's poses).
+ESAC_HD void bearing(float u, float v, double f, double ppx, double ppy, double y[3]) {
+    const double ifx = 1. / f;
+    double bx = (double)(float)(((double)u - ppx) * ifx), by = (double)(float)(((double)v - ppy) * ifx);
+    double n = 1. / sqrt(bx * bx + by * by + 1.);
+    y[0] = bx * n; y[1] = by * n; y[2] = n;
 }
 
 // solvePnP(4 points, SOLVEPNP_P3P) semantics: solve with the first three correspondences, pick the
@@ -594,12 +675,7 @@ ESAC_HDN int p3p_solve(const double y[3][3], const double x[3][3], double Rs[4][
 ESAC_HD bool p3p_pose(const float obj[4][3], const float img[4][2], double f, double ppx, double ppy, Pose& pose) {
     double y[3][3], x[3][3];
     for (int i = 0; i < 3; ++i) {
-        // cv::solvePnP hands P3P the output of undistortPoints on float points: (u - cx) * (1/fx) rounded to
-        // float (a ~1e-5 px perturbation of the image points that shows up in the 4.13 oracle's poses).
-        const double ifx = 1. / f;
-        double bx = (double)(float)(((double)img[i][0] - ppx) * ifx), by = (double)(float)(((double)img[i][1] - ppy) * ifx);
-        double n = 1. / sqrt(bx * bx + by * by + 1.);
-        y[i][0] = bx * n; y[i][1] = by * n; y[i][2] = n;
+        bearing(img[i][0], img[i][1], f, ppx, ppy, y[i]);
         for (int c = 0; c < 3; ++c) x[i][c] = (double)obj[i][c];
     }
     double Rs[4][9], ts[4][3];
@@ -620,6 +696,42 @@ ESAC_HD bool p3p_pose(const float obj[4][3], const float img[4][2], double f, do
     rodrigues_m2v(Rs[best], pose.r);
     pose.t[0] = ts[best][0]; pose.t[1] = ts[best][1]; pose.t[2] = ts[best][2];
     return true;
+}
+
+// Float rejection prefilter for a sampling try.  Returns false only when the try is certain to fail the
+// 4-point gate (every P3P root reprojects the 4th point farther than `margin` times the inlier threshold and no
+// numerical decision was borderline); true means "run the exact fp64 path".  Never the final word on accept.
+ESAC_HD bool p3p_may_pass(const float obj[4][3], const float img[4][2], float f, float ppx, float ppy, float tau,
+                          float margin = 4.f) {
+    float y[3][3], x[3][3], x3[3];
+    const float ifx = 1.f / f;
+    for (int i = 0; i < 3; ++i) {
+        float bx = (img[i][0] - ppx) * ifx, by = (img[i][1] - ppy) * ifx;
+        float n = rsqrtf(bx * bx + by * by + 1.f);
+        y[i][0] = bx * n; y[i][1] = by * n; y[i][2] = n;
+        for (int c = 0; c < 3; ++c) x[i][c] = obj[i][c] - obj[0][c];  // recentre: float differences of float inputs
+    }
+    for (int c = 0; c < 3; ++c) x3[c] = obj[3][c] - obj[0][c];
+    float lam[4][3], amax, cs[3], ss[3];
+    bool unc;
+    int n = p3p_lambdas<float>(y, x, lam, amax, cs, ss, unc);
+    if (unc || !(amax == amax)) return true;
+    const float lim = margin * tau, lim2 = lim * lim;
+    const float sa = sqrtf(amax);
+    for (int s = 0; s < n; ++s) {
+        float P[3][3], R[9], t[3];
+        for (int i = 0; i < 3; ++i)
+            for (int c = 0; c < 3; ++c) P[i][c] = lam[s][i] * sa * y[i][c];
+        if (!align_triangles<float>(P, x, R, t)) return true;
+        float xc = R[0] * x3[0] + R[1] * x3[1] + R[2] * x3[2] + t[0];
+        float yc = R[3] * x3[0] + R[4] * x3[1] + R[5] * x3[2] + t[1];
+        float zc = R[6] * x3[0] + R[7] * x3[1] + R[8] * x3[2] + t[2];
+        float iz = 1.f / zc;
+        float du = ppx + f * xc * iz - img[3][0], dv = ppy + f * yc * iz - img[3][1];
+        float e = du * du + dv * dv;
+        if (!(e > lim2)) return true;  // close enough (or NaN/inf): let the exact path decide
+    }
+    return false;
 }
 
 // The reference's 4-point gate (esac_util.h:202-223): every minimal-set point must reproject within

@@ -53,12 +53,24 @@ __global__ void __launch_bounds__(1024) prep_kernel(const float* __restrict__ co
             *n_chunks = nc;
         }
         __syncthreads();
-        // stable permutation: thread e walks the hypotheses in order
-        for (int e = tid; e < P.E; e += blockDim.x) {
-            if (counts[e] == 0) continue;
-            int pos = offsets[e];
-            for (int h = 0; h < P.M; ++h)
-                if (assign32[h] == e) { perm[pos] = h; slot_of[h] = pos; ++pos; }
+        // stable permutation: warp w ranks the hypotheses of expert e = w, w + nwarps, ... with ballots
+        {
+            const int lane = tid & 31, warp = tid >> 5, nwarps = blockDim.x >> 5;
+            for (int e = warp; e < P.E; e += nwarps) {
+                if (counts[e] == 0) continue;
+                int pos = offsets[e];
+                for (int b = 0; b < P.M; b += 32) {
+                    const int h = b + lane;
+                    const bool mine = h < P.M && assign32[h] == e;
+                    const unsigned m = __ballot_sync(0xffffffffu, mine);
+                    if (mine) {
+                        const int q = pos + __popc(m & ((1u << lane) - 1u));
+                        perm[q] = h;
+                        slot_of[h] = q;
+                    }
+                    pos += __popc(m);
+                }
+            }
         }
     } else {
         // plane centre: mean of a strided sample (only conditions the fp32 arithmetic)
@@ -295,24 +307,28 @@ void launch_score(const ScoreArgs& a, int ppt, int grid, cudaStream_t st) {
 // ---------------------------------------------------------------------------------------------
 // select: finish scores, softMax, entropy, argmax (draw with training=false), contributing list
 // ---------------------------------------------------------------------------------------------
+// scores[h] = (alpha/W/H) * sum over tiles of the partial soft-inlier sums: one warp per hypothesis, fixed order
+__global__ void __launch_bounds__(256) finish_scores_kernel(const float* __restrict__ part, const int* __restrict__ slot_of,
+                                                            Problem P, int T, double* scores) {
+    const int lane = threadIdx.x & 31;
+    const int h = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (h >= P.M) return;
+    // getHypScores' final factor is a float expression: alpha / cols / rows (esac_util.h:256)
+    const float facf = P.alpha / (float)P.W / (float)P.H;
+    const float* row = part + (size_t)slot_of[h] * T;
+    double s = 0;
+    for (int t = lane; t < T; t += 32) s += (double)row[t];
+    for (int o = 16; o; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if (lane == 0) scores[h] = s * (double)facf;
+}
+
 __global__ void __launch_bounds__(1024) select_kernel(const float* __restrict__ part, const int* __restrict__ slot_of,
                                                       Problem P, int T, double* scores, double* probs, double* stats,
                                                       int* winner, int* contrib, int* n_contrib) {
     __shared__ double sred[32];
     __shared__ int sidx[32];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nw = blockDim.x >> 5;
-    // getHypScores' final factor is a float expression: alpha / cols / rows (esac_util.h:256)
-    const float facf = P.alpha / (float)P.W / (float)P.H;
-    const double fac = (double)facf;
-    // one warp per hypothesis: fixed-order fp64 sum of the tile partials
-    for (int h = warp; h < P.M; h += nw) {
-        const float* row = part + (size_t)slot_of[h] * T;
-        double s = 0;
-        for (int t = lane; t < T; t += 32) s += (double)row[t];
-        for (int o = 16; o; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-        if (lane == 0) scores[h] = s * fac;
-    }
-    __syncthreads();
+    (void)part; (void)slot_of; (void)T;
     // max
     double mx = -1e300;
     for (int h = tid; h < P.M; h += blockDim.x) mx = fmax(mx, scores[h]);
@@ -353,6 +369,8 @@ __global__ void __launch_bounds__(1024) select_kernel(const float* __restrict__ 
     __shared__ double sent[32];
     if (lane == 0) sent[warp] = ent;
     __syncthreads();
+    __shared__ int swc[32];
+    __shared__ int srun;
     if (tid == 0) {
         double b = -1; int i = 0x7fffffff; double en = 0;
         for (int w = 0; w < nw; ++w) {
@@ -361,16 +379,30 @@ __global__ void __launch_bounds__(1024) select_kernel(const float* __restrict__ 
         }
         if (i == 0x7fffffff) i = 0;
         *winner = i;
-        int nc = 0;
-        for (int h = 0; h < P.M; ++h)
-            if (!(probs[h] < kProbThresh)) contrib[nc++] = h;
-        *n_contrib = nc;
-        stats[0] = en; stats[1] = (double)i; stats[2] = (double)nc;
+        stats[0] = en; stats[1] = (double)i;
+        srun = 0;
     }
+    __syncthreads();
+    // ordered compaction of the hypotheses with p >= PROB_THRESH (esac.cpp:334, esac_derivative.h:231)
+    for (int b = 0; b < P.M; b += blockDim.x) {
+        const int h = b + tid;
+        const bool flag = h < P.M && !(probs[h] < kProbThresh);
+        const unsigned m = __ballot_sync(0xffffffffu, flag);
+        if (lane == 0) swc[warp] = __popc(m);
+        __syncthreads();
+        int off = srun;
+        for (int w = 0; w < warp; ++w) off += swc[w];
+        if (flag) contrib[off + __popc(m & ((1u << lane) - 1u))] = h;
+        __syncthreads();
+        if (tid == 0) { int t = 0; for (int w = 0; w < nw; ++w) t += swc[w]; srun += t; }
+        __syncthreads();
+    }
+    if (tid == 0) { *n_contrib = srun; stats[2] = (double)srun; }
 }
 
 void launch_select(const float* part, const int* slot_of, const Problem& P, int T, double* scores, double* probs,
                    double* stats, int* winner, int* contrib, int* n_contrib, cudaStream_t st) {
+    finish_scores_kernel<<<(P.M * 32 + 255) / 256, 256, 0, st>>>(part, slot_of, P, T, scores);
     select_kernel<<<1, 1024, 0, st>>>(part, slot_of, P, T, scores, probs, stats, winner, contrib, n_contrib);
 }
 

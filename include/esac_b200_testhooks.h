@@ -22,6 +22,10 @@ int esacb200_host_p3p_all(const double* y9, const double* x9, double* Rs36, doub
  * Returns 1 when a pose was found.  *gate = result of the 4-point reprojection gate (esac_util.h:202-223). */
 int esacb200_host_p3p_pose(const float* obj12, const float* img8, float f, float ppx, float ppy, float tau,
                            double* pose6, int* gate);
+/* One sampling try on given correspondences: *may_pass = float prefilter verdict (0 = certainly rejected),
+ * *accept = exact verdict (P3P solved and the 4-point gate passed).  Invariant: accept implies may_pass. */
+void esacb200_host_try(const float* obj12, const float* img8, float f, float ppx, float ppy, float tau, float margin,
+                       int* may_pass, int* accept);
 /* cv::projectPoints for one point: float-rounded pixel + fp64 pixel + 2x6 Jacobian (rvec | tvec columns). */
 void esacb200_host_project(const double pose6[6], float f, float ppx, float ppy, const float X[3], float uv_f[2],
                            double uv[2], double J12[12]);

@@ -200,3 +200,31 @@ def test_cell_stream_matches_oracle(lib):
                 assert cells.reshape(4, 2).tolist() == [list(c) for c in ref]
                 assert cells.reshape(4, 2)[:, 0].max() <= W - 2 and cells.reshape(4, 2)[:, 1].max() <= H - 2
                 assert len({tuple(c) for c in cells.reshape(4, 2)}) == 4
+
+
+@pytest.mark.parametrize("kw,which", [({"seed": 1}, "gt"), ({"seed": 1, "active_only": False}, "other"),
+                                      ({"seed": 3, "outdoor": True}, "gt"), ({"seed": 2, "world_offset": 700.0}, "gt")])
+def test_float_prefilter_never_rejects_an_accepted_try(lib, kw, which):
+    """The sampling kernel's float prefilter (p3p_may_pass) may only discard tries the exact fp64 path rejects."""
+    from esac_b200.synth import make_scene
+    sc = make_scene(E=2, H=60, W=80, M=8, sub=8, **kw)
+    e = sc.gt_expert if which == "gt" else 1 - sc.gt_expert
+    rng = np.random.default_rng(5)
+    pl = sc.coords[e]
+    mp, ac = C.c_int(), C.c_int()
+    n_acc = n_may = 0
+    n = 20000
+    for _ in range(n):
+        while True:
+            xs = rng.integers(0, 79, 4); ys = rng.integers(0, 59, 4)
+            if len({(a, b) for a, b in zip(xs, ys)}) == 4:
+                break
+        obj = np.ascontiguousarray(pl[:, ys, xs].T.astype(np.float32))
+        img = np.ascontiguousarray(np.stack([xs * 8 + 4, ys * 8 + 4], 1).astype(np.float32))
+        lib.esacb200_host_try(_ptr(obj), _ptr(img), sc.f, sc.ppx, sc.ppy, sc.tau, 4.0, C.byref(mp), C.byref(ac))
+        assert not (ac.value and not mp.value)
+        n_acc += ac.value; n_may += mp.value
+    if which == "gt":
+        assert n_acc > 500           # the invariant was exercised on accepted tries
+    else:
+        assert n_may < 0.1 * n       # and the prefilter does reject most tries on wrong experts
