@@ -139,12 +139,9 @@ __device__ __forceinline__ double score_weight(float err_clamped, const Problem&
 __device__ __forceinline__ void block_reduce_store(double (&v)[kRed], double* dst) {
     __shared__ double sred[kBwdThreads / 32][kRed];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-#pragma unroll
-    for (int i = 0; i < kRed; ++i) {
-        double s = v[i];
-#pragma unroll
-        for (int o = 16; o; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-        if (lane == 0) sred[warp][i] = s;
+    {
+        const double s = warp_reduce_scatter<kRed>(v);
+        if (lane < kRed) sred[warp][lane] = s;
     }
     __syncthreads();
     if (threadIdx.x < kRed) {

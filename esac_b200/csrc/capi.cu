@@ -63,7 +63,7 @@ struct esacb200_ctx {
     // workspace
     DevBuf coords, grads, assign64, assign32, counts, offsets, perm, slot_of, chunks, scalars, centres, poses, poses_ref,
         cells, tries, posepk, part, scores, probs, stats, contrib, masks, rounds, scratch, barrier, out17, inject,
-        losses, red, hypgrad, job_of, gt;
+        losses, red, hypgrad, job_of, gt, smp_int, smp_surv;
     float* h_out = nullptr;  // pinned staging: 32 floats
     double* h_dbl = nullptr; // pinned staging: 8 doubles
     int inj_M = 0, inj_T = 0;
@@ -209,6 +209,25 @@ int stage_inputs(esacb200_ctx* ctx, Plan& pl, const float* coords, const int64_t
     return 0;
 }
 
+int run_sample(esacb200_ctx* ctx, const Plan& pl, uint64_t seed) {
+    const Problem& P = pl.P;
+    const int cap = 1 << 20;
+    CK(ctx->smp_int.ensure(((size_t)P.M * 5 + 8) * 4));
+    CK(ctx->smp_surv.ensure((size_t)cap * sizeof(int2)));
+    SampleState st;
+    int* b = ctx->smp_int.as<int>();
+    st.best = b; st.base = b + P.M; st.ovf = b + 2 * (size_t)P.M; st.list = b + 3 * (size_t)P.M; st.counters = b + 5 * (size_t)P.M;
+    st.surv = ctx->smp_surv.as<int2>();
+    st.cap = cap;
+    st.M = P.M;
+    ctx->st.kernel_launches += launch_sample(pl.d_coords, ctx->assign32.as<int>(), P, seed, ctx->max_tries,
+                                             ctx->inj_M ? ctx->inject.as<int>() : nullptr, ctx->inj_T, st, ctx->sm_count,
+                                             ctx->poses.as<Pose>(), ctx->cells.as<int>(), ctx->tries.as<int>(), ctx->stream);
+    CK(cudaGetLastError());
+    mark(ctx, EV_SAMPLE);
+    return 0;
+}
+
 int run_score(esacb200_ctx* ctx, const Plan& pl) {
     const Problem& P = pl.P;
     int* sc = ctx->scalars.as<int>();
@@ -268,6 +287,7 @@ int run_refine(esacb200_ctx* ctx, const Plan& pl, const Pose* in, Pose* out, con
     CK(cudaMemsetAsync(ctx->barrier.p, 0, (size_t)n_groups * 4, ctx->stream));
     RefineArgs a;
     a.coords = pl.d_coords;
+    a.centres = ctx->centres.as<float>();
     a.assign32 = ctx->assign32.as<int>();
     a.poses_in = in;
     a.poses_out = out;
@@ -356,7 +376,7 @@ void esacb200_destroy(esacb200_ctx* ctx) {
                       &ctx->slot_of, &ctx->chunks, &ctx->scalars, &ctx->centres, &ctx->poses, &ctx->poses_ref, &ctx->cells,
                       &ctx->tries, &ctx->posepk, &ctx->part, &ctx->scores, &ctx->probs, &ctx->stats, &ctx->contrib,
                       &ctx->masks, &ctx->rounds, &ctx->scratch, &ctx->barrier, &ctx->out17, &ctx->inject, &ctx->losses,
-                      &ctx->red, &ctx->hypgrad, &ctx->job_of, &ctx->gt};
+                      &ctx->red, &ctx->hypgrad, &ctx->job_of, &ctx->gt, &ctx->smp_int, &ctx->smp_surv};
     for (DevBuf* b : bufs) b->release();
     for (int i = 0; i < EV_COUNT; ++i)
         if (ctx->ev[i]) cudaEventDestroy(ctx->ev[i]);
@@ -428,10 +448,8 @@ int esacb200_forward(esacb200_ctx* ctx, const float* coords, int E, int H, int W
     const Problem& P = pl.P;
     int* sc = ctx->scalars.as<int>();
     const uint64_t seed = call_seed(ctx);
-    launch_sample(pl.d_coords, ctx->assign32.as<int>(), P, seed, ctx->max_tries, ctx->inj_M ? ctx->inject.as<int>() : nullptr,
-                  ctx->inj_T, ctx->poses.as<Pose>(), ctx->cells.as<int>(), ctx->tries.as<int>(), ctx->stream);
-    ctx->st.kernel_launches += 1;
-    mark(ctx, EV_SAMPLE);
+    rc = run_sample(ctx, pl, seed);
+    if (rc) return rc;
     rc = run_score(ctx, pl);
     if (rc) return rc;
     const int group = pick_group(ctx, P, 1);
@@ -574,10 +592,8 @@ int esacb200_backward(esacb200_ctx* ctx, const float* coords, float* grads, int 
     if (rc) return rc;
     int* sc = ctx->scalars.as<int>();
     const uint64_t seed = call_seed(ctx);
-    launch_sample(pl.d_coords, ctx->assign32.as<int>(), P, seed, ctx->max_tries, ctx->inj_M ? ctx->inject.as<int>() : nullptr,
-                  ctx->inj_T, ctx->poses.as<Pose>(), ctx->cells.as<int>(), ctx->tries.as<int>(), ctx->stream);
-    ctx->st.kernel_launches += 1;
-    mark(ctx, EV_SAMPLE);
+    rc = run_sample(ctx, pl, seed);
+    if (rc) return rc;
     rc = run_score(ctx, pl);
     if (rc) return rc;
     // refHyps = initHyps for everything below PROB_THRESH (esac.cpp:331-334)

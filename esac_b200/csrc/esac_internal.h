@@ -7,6 +7,30 @@
 
 namespace esacb200 {
 
+#ifdef __CUDACC__
+// Warp reduce-scatter of NV <= 32 doubles per lane: lane L returns the warp total of value L (0 for L >= NV).
+// A transposing butterfly: 31 double shuffles instead of 5*NV.
+template <int NV>
+__device__ __forceinline__ double warp_reduce_scatter(const double (&v)[NV]) {
+    static_assert(NV <= 32, "at most 32 values");
+    const int lane = threadIdx.x & 31;
+    double w[32];
+#pragma unroll
+    for (int i = 0; i < 32; ++i) w[i] = i < NV ? v[i] : 0.0;
+#pragma unroll
+    for (int o = 16; o >= 1; o >>= 1) {
+        const bool up = (lane & o) != 0;
+#pragma unroll
+        for (int i = 0; i < o; ++i) {
+            const double keep = up ? w[i + o] : w[i];
+            const double send = up ? w[i] : w[i + o];
+            w[i] = keep + __shfl_xor_sync(0xffffffffu, send, o);
+        }
+    }
+    return w[0];
+}
+#endif
+
 // Per-call problem description (esac.cpp:64-77 arguments + tensor sizes).
 struct Problem {
     int E, H, W, N, M;
@@ -26,10 +50,10 @@ struct ChunkDesc {
     int pad;
 };
 
-// Folded fp32 pose for the scoring kernel: rows of diag(f,f,1)*R and diag(f,f,1)*(R*c + t), every
-// value stored twice so one LDS.128 yields two aligned f32x2 operands.
+// Folded fp32 pose for the scoring kernel: rows [A_r0 A_r1 A_r2 | b_r] of diag(f,f,1)*R and
+// diag(f,f,1)*(R*c + t); FFMA2 broadcasts a scalar register operand to both f32x2 lanes.
 struct PosePk {
-    float4 v[6];
+    float4 v[3];
 };
 
 struct ScoreArgs {
@@ -63,14 +87,28 @@ void launch_select(const float* part, const int* slot_of, const Problem& P, int 
                    int* n_contrib, cudaStream_t st);
 
 // --- hyp.cu -------------------------------------------------------------------------------
-void launch_sample(const float* coords, const int* assign32, const Problem& P, uint64_t seed, int max_tries,
-                   const int* injected, int inj_T, Pose* poses, int* cells, int* tries, cudaStream_t st);
+// Work state of the sampling waves (all device memory, M = hypotheses).
+struct SampleState {
+    int* best;      // [M] lowest accepted try (0x7fffffff = none yet)
+    int* base;      // [M] first try not judged yet
+    int* ovf;       // [M] lowest survivor that did not fit the list in the current wave
+    int* list;      // [2M] unresolved hypotheses (second half: scratch for rebuilding)
+    int2* surv;     // [cap] (hypothesis, try) pairs that passed the float prefilter
+    int cap;
+    int* counters;  // [0] unresolved, [1] survivors
+    int M;
+};
+// Returns the number of kernel launches it enqueued.
+int launch_sample(const float* coords, const int* assign32, const Problem& P, uint64_t seed, int max_tries,
+                  const int* injected, int inj_T, const SampleState& st, int sm_count, Pose* poses, int* cells, int* tries,
+                  cudaStream_t st_);
 
 // --- refine.cu ----------------------------------------------------------------------------
 // Refines poses_in[jobs[j]] -> poses_out[jobs[j]] for j < *n_jobs (device scalar) or n_jobs_host.
 // masks: [job][ceil(N/32)] final inlier bit masks (may be null), rounds: [job] accepted rounds.
 struct RefineArgs {
     const float* coords;
+    const float* centres;    // [E,3] plane centres (prep kernel)
     const int* assign32;
     const Pose* poses_in;
     Pose* poses_out;

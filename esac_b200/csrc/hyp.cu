@@ -1,29 +1,51 @@
-// Hypothesis sampling: minimal sets -> P3P -> 4-point gate, one CTA per hypothesis.
+// Hypothesis sampling: minimal sets -> P3P -> 4-point gate.
 //
-// Replaces sampleHypotheses (esac_util.h:129-225, called from esac.cpp:112 / 276).  The reference loops
-// tries sequentially per hypothesis under `omp parallel for`; the counter-based stream (esac_rng.cuh) makes
-// every try addressable, so a CTA evaluates a contiguous block of tries at once and keeps the LOWEST passing
-// try -- exactly the try the sequential loop would have stopped at.  Maps whose experts are wrong need
-// ~1/P(4th point lands within tau) ~ 1e3 tries per hypothesis (the dominant cost of a step), so each try
-// first goes through a float prefilter (p3p_may_pass) that discards the >98% of tries whose every P3P root
-// misses the 4th point by more than 4 tau; only the survivors are compacted and run through the exact
-// fp64 path (p3p_pose + minimal_set_gate) whose verdict is the only one that counts.
+// Replaces sampleHypotheses (esac_util.h:129-225, called from esac.cpp:112 / 276).  The reference loops tries
+// sequentially per hypothesis under `omp parallel for`; the counter-based stream (esac_rng.cuh) makes every try
+// addressable, so tries are evaluated in bulk and the LOWEST passing try of each hypothesis is kept -- exactly the
+// try the sequential loop would have stopped at.  Wrong experts need ~1/P(4th point lands within tau) ~ 1e3 tries
+// per hypothesis, which makes this the most expensive stage of a step; it runs as waves of small kernels:
+//
+//   wave r (try window [base_h, base_h + span_r) of every unresolved hypothesis, span = 128, 1024, 8192, 32768):
+//     prefilter_kernel   one thread per try, fp32 only: p3p_may_pass() discards tries whose every P3P root misses
+//                        the 4th point by > 4 tau (>95% on wrong experts); survivors are appended to a global list
+//     exact_kernel       one thread per survivor: the fp64 path (p3p_pose + minimal_set_gate) whose verdict is the
+//                        only one that counts; atomicMin keeps the lowest accepted try per hypothesis
+//     advance_kernel     marks resolved hypotheses, advances the window of the others, rebuilds the work list
+//   tail_kernel          CTA per still-unresolved hypothesis: same two phases inside one CTA up to max_tries
+//   emit_kernel          one thread per hypothesis: re-derives the winning (or, when exhausted, the last) try and
+//                        writes pose / cells / try count
+//
+// Keeping the float and double paths in different kernels matters: fused, the kernel ran at 10% issue utilisation,
+// stalled on instruction fetch (profiles/r01b_sample_kernel_ncu.json).
 #include "esac_internal.h"
 #include "esac_rng.cuh"
 
 namespace esacb200 {
 
-constexpr int kSampleThreads = 128;
-constexpr int kSampleMaxK = 8;  // tries per thread per super-round
+constexpr int kTryThreads = 128;
+constexpr int kNoTry = 0x7fffffff;
 
-__device__ __forceinline__ void load_try(const float* __restrict__ pl, const Problem& P, const int* injected, int inj_T,
-                                         uint64_t seed, int h, int t, int cx[4], int cy[4], float obj[4][3], float img[4][2]) {
-    if (injected) {
-        const int* c = injected + ((size_t)h * inj_T + t) * 8;
+struct SampleArgs {
+    const float* coords;
+    const int* assign32;
+    Problem P;
+    uint64_t seed;
+    int limit;            // tries allowed per hypothesis
+    const int* injected;  // [M][inj_T][4][2] or null
+    int inj_T;
+    SampleState st;
+};
+
+__device__ __forceinline__ void load_try(const SampleArgs& a, int h, int t, int cx[4], int cy[4], float obj[4][3], float img[4][2]) {
+    const Problem& P = a.P;
+    if (a.injected) {
+        const int* c = a.injected + ((size_t)h * a.inj_T + t) * 8;
         for (int j = 0; j < 4; ++j) { cx[j] = c[2 * j]; cy[j] = c[2 * j + 1]; }
     } else {
-        draw_minimal_set(seed, (uint32_t)h, (uint32_t)t, P.W, P.H, cx, cy);
+        draw_minimal_set(a.seed, (uint32_t)h, (uint32_t)t, P.W, P.H, cx, cy);
     }
+    const float* pl = a.coords + (size_t)a.assign32[h] * 3 * P.N;
     for (int j = 0; j < 4; ++j) {
         const int p = cy[j] * P.W + cx[j];
         obj[j][0] = pl[p]; obj[j][1] = pl[P.N + p]; obj[j][2] = pl[2 * (size_t)P.N + p];
@@ -32,68 +54,170 @@ __device__ __forceinline__ void load_try(const float* __restrict__ pl, const Pro
     }
 }
 
-__global__ void __launch_bounds__(kSampleThreads) sample_kernel(const float* __restrict__ coords, const int* __restrict__ assign32,
-                                                                Problem P, uint64_t seed, int max_tries,
-                                                                const int* __restrict__ injected, int inj_T, Pose* poses,
-                                                                int* cells, int* tries) {
-    const int h = blockIdx.x;
-    const int tid = threadIdx.x;
-    const int e = assign32[h];
-    const float* pl = coords + (size_t)e * 3 * P.N;
-    const int limit = injected ? min(max_tries, inj_T) : max_tries;
-    const double f = (double)P.f, ppx = (double)P.ppx, ppy = (double)P.ppy;
-    __shared__ int s_list[kSampleThreads * kSampleMaxK];
-    __shared__ int s_n, s_best;
-    if (tid == 0) { s_best = 0x7fffffff; }
-    int base = 0;
-    int K = 1;  // first super-round: one try per thread (easy maps finish here), then kSampleMaxK
-    while (base < limit) {
-        if (tid == 0) s_n = 0;
-        __syncthreads();
-        const int span = min(limit - base, K * kSampleThreads);
-        // ---- float prefilter over [base, base + span) ----
-        for (int t = base + tid; t < base + span; t += kSampleThreads) {
+__device__ __noinline__ bool exact_try(const SampleArgs& a, int h, int t, Pose& pose, int cx[4], int cy[4], bool& solved) {
+    float obj[4][3], img[4][2];
+    load_try(a, h, t, cx, cy, obj, img);
+    const double f = (double)a.P.f, ppx = (double)a.P.ppx, ppy = (double)a.P.ppy;
+    solved = p3p_pose(obj, img, f, ppx, ppy, pose);
+    return solved && minimal_set_gate(obj, img, pose, f, ppx, ppy, a.P.tau);
+}
+
+// state init: every hypothesis unresolved, window at try 0
+__global__ void sample_init_kernel(SampleState st, int M) {
+    const int h = blockIdx.x * blockDim.x + threadIdx.x;
+    if (h < M) { st.best[h] = kNoTry; st.base[h] = 0; st.ovf[h] = kNoTry; st.list[h] = h; }
+    if (h == 0) { st.counters[0] = M; st.counters[1] = 0; st.counters[2] = 0; }  // n_unresolved, n_survivors, next-list fill
+}
+
+// ---- wave phase 1: fp32 prefilter, one thread per try --------------------------------------------------------
+__global__ void __launch_bounds__(kTryThreads) prefilter_kernel(const __grid_constant__ SampleArgs a, int span) {
+    const int n_unres = a.st.counters[0];
+    const int cph = (span + kTryThreads - 1) / kTryThreads;  // chunks per hypothesis
+    const long long n_items = (long long)n_unres * cph;
+    const int lane = threadIdx.x & 31;
+    for (long long item = blockIdx.x; item < n_items; item += gridDim.x) {
+        const int u = (int)(item / cph), c = (int)(item - (long long)u * cph);
+        const int h = a.st.list[u];
+        const int t0 = a.st.base[h];
+        const int off = c * kTryThreads + threadIdx.x;
+        const int t = t0 + off;
+        bool pass = false;
+        if (off < span && t < a.limit) {
             int cx[4], cy[4];
             float obj[4][3], img[4][2];
-            load_try(pl, P, injected, inj_T, seed, h, t, cx, cy, obj, img);
-            if (p3p_may_pass(obj, img, P.f, P.ppx, P.ppy, P.tau)) s_list[atomicAdd(&s_n, 1)] = t;
+            load_try(a, h, t, cx, cy, obj, img);
+            pass = p3p_may_pass(obj, img, a.P.f, a.P.ppx, a.P.ppy, a.P.tau);
         }
-        __syncthreads();
-        // ---- exact path on the survivors ----
-        const int n = s_n;
-        for (int i = tid; i < n; i += kSampleThreads) {
-            const int t = s_list[i];
-            int cx[4], cy[4];
-            float obj[4][3], img[4][2];
-            load_try(pl, P, injected, inj_T, seed, h, t, cx, cy, obj, img);
-            Pose pose;
-            if (p3p_pose(obj, img, f, ppx, ppy, pose) && minimal_set_gate(obj, img, pose, f, ppx, ppy, P.tau)) atomicMin(&s_best, t);
+        // warp-aggregated append of the survivors
+        const unsigned m = __ballot_sync(0xffffffffu, pass);
+        if (m) {
+            int basei = 0;
+            if (lane == __ffs(m) - 1) basei = atomicAdd(&a.st.counters[1], __popc(m));
+            basei = __shfl_sync(0xffffffffu, basei, __ffs(m) - 1);
+            if (pass) {
+                const int idx = basei + __popc(m & ((1u << lane) - 1u));
+                if (idx < a.st.cap) a.st.surv[idx] = make_int2(h, t);
+                else atomicMin(&a.st.ovf[h], t);  // list full: this hypothesis resumes from here in the next wave
+            }
         }
-        __syncthreads();
-        if (s_best != 0x7fffffff) break;
-        base += span;
-        K = kSampleMaxK;
-    }
-    // one thread re-derives the winning try (or, when exhausted, the last try whose state survives in the reference)
-    if (tid == 0) {
-        const bool found = s_best != 0x7fffffff;
-        const int t = found ? s_best : limit - 1;
-        int cx[4], cy[4];
-        float obj[4][3], img[4][2];
-        load_try(pl, P, injected, inj_T, seed, h, t, cx, cy, obj, img);
-        Pose pose;
-        if (!p3p_pose(obj, img, f, ppx, ppy, pose)) {
-            for (int c = 0; c < 3; ++c) { pose.r[c] = 0; pose.t[c] = 0; }  // safeSolvePnP failure state
-        }
-        poses[h] = pose;
-        for (int j = 0; j < 4; ++j) { cells[h * 8 + 2 * j] = cx[j]; cells[h * 8 + 2 * j + 1] = cy[j]; }
-        tries[h] = t + 1;
     }
 }
 
-void launch_sample(const float* coords, const int* assign32, const Problem& P, uint64_t seed, int max_tries,
-                   const int* injected, int inj_T, Pose* poses, int* cells, int* tries, cudaStream_t st) {
-    sample_kernel<<<P.M, kSampleThreads, 0, st>>>(coords, assign32, P, seed, max_tries, injected, inj_T, poses, cells, tries);
+// ---- wave phase 2: exact fp64 verdict on the survivors -------------------------------------------------------
+__global__ void __launch_bounds__(128) exact_kernel(const __grid_constant__ SampleArgs a) {
+    const int n = min(a.st.counters[1], a.st.cap);
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const int2 ht = a.st.surv[i];
+        if (ht.y >= a.st.ovf[ht.x]) continue;  // beyond the point where the list overflowed: redone next wave
+        Pose pose;
+        int cx[4], cy[4];
+        bool solved;
+        if (exact_try(a, ht.x, ht.y, pose, cx, cy, solved)) atomicMin(&a.st.best[ht.x], ht.y);
+    }
+}
+
+// ---- wave phase 3: bookkeeping ------------------------------------------------------------------------------
+__global__ void __launch_bounds__(1024) advance_kernel(SampleState st, int span, int limit) {
+    __shared__ int s_fill;
+    if (threadIdx.x == 0) s_fill = 0;
+    __syncthreads();
+    const int n_unres = st.counters[0];
+    // the next list is built in the second half of the buffer, then copied back (single CTA: no races)
+    int* next = st.list + st.M;
+    for (int u = threadIdx.x; u < n_unres; u += blockDim.x) {
+        const int h = st.list[u];
+        const int ovf = st.ovf[h];
+        const int end = min(st.base[h] + span, ovf);  // tries below `end` have all been judged
+        const bool resolved = st.best[h] < end;
+        if (!resolved) {
+            if (st.best[h] != kNoTry) st.best[h] = kNoTry;  // an accept beyond an overflow hole does not count yet
+            st.base[h] = end;
+            st.ovf[h] = kNoTry;
+            if (end < limit) next[atomicAdd(&s_fill, 1)] = h;
+        }
+    }
+    __syncthreads();
+    const int nn = s_fill;
+    for (int u = threadIdx.x; u < nn; u += blockDim.x) st.list[u] = next[u];
+    __syncthreads();
+    if (threadIdx.x == 0) { st.counters[0] = nn; st.counters[1] = 0; }
+}
+
+// ---- tail: CTA per unresolved hypothesis, both phases inside the CTA, up to the try limit --------------------
+__global__ void __launch_bounds__(kTryThreads) tail_kernel(const __grid_constant__ SampleArgs a) {
+    const int n_unres = a.st.counters[0];
+    __shared__ int s_list[kTryThreads * 8];
+    __shared__ int s_n, s_best;
+    for (int u = blockIdx.x; u < n_unres; u += gridDim.x) {
+        const int h = a.st.list[u];
+        int base = a.st.base[h];
+        __syncthreads();
+        if (threadIdx.x == 0) s_best = kNoTry;
+        while (base < a.limit) {
+            if (threadIdx.x == 0) s_n = 0;
+            __syncthreads();
+            const int span = min(a.limit - base, kTryThreads * 8);
+            for (int t = base + threadIdx.x; t < base + span; t += kTryThreads) {
+                int cx[4], cy[4];
+                float obj[4][3], img[4][2];
+                load_try(a, h, t, cx, cy, obj, img);
+                if (p3p_may_pass(obj, img, a.P.f, a.P.ppx, a.P.ppy, a.P.tau)) s_list[atomicAdd(&s_n, 1)] = t;
+            }
+            __syncthreads();
+            const int n = s_n;
+            for (int i = threadIdx.x; i < n; i += kTryThreads) {
+                Pose pose;
+                int cx[4], cy[4];
+                bool solved;
+                if (exact_try(a, h, s_list[i], pose, cx, cy, solved)) atomicMin(&s_best, s_list[i]);
+            }
+            __syncthreads();
+            if (s_best != kNoTry) break;
+            base += span;
+        }
+        if (threadIdx.x == 0 && s_best != kNoTry) a.st.best[h] = s_best;
+    }
+}
+
+// ---- emit: pose / cells / try count of every hypothesis ------------------------------------------------------
+__global__ void __launch_bounds__(64) emit_kernel(const __grid_constant__ SampleArgs a, Pose* poses, int* cells, int* tries) {
+    const int h = blockIdx.x * blockDim.x + threadIdx.x;
+    if (h >= a.P.M) return;
+    const int b = a.st.best[h];
+    const int t = b != kNoTry ? b : a.limit - 1;  // exhausted: the state of the last try survives (esac_util.h:154-224)
+    Pose pose;
+    int cx[4], cy[4];
+    bool solved;
+    exact_try(a, h, t, pose, cx, cy, solved);
+    if (!solved) { for (int c = 0; c < 3; ++c) { pose.r[c] = 0; pose.t[c] = 0; } }  // safeSolvePnP failure state
+    poses[h] = pose;
+    for (int j = 0; j < 4; ++j) { cells[h * 8 + 2 * j] = cx[j]; cells[h * 8 + 2 * j + 1] = cy[j]; }
+    tries[h] = t + 1;
+}
+
+int launch_sample(const float* coords, const int* assign32, const Problem& P, uint64_t seed, int max_tries,
+                  const int* injected, int inj_T, const SampleState& st, int sm_count, Pose* poses, int* cells, int* tries,
+                  cudaStream_t stream) {
+    SampleArgs a;
+    a.coords = coords; a.assign32 = assign32; a.P = P; a.seed = seed;
+    a.limit = injected ? (max_tries < inj_T ? max_tries : inj_T) : max_tries;
+    a.injected = injected; a.inj_T = inj_T; a.st = st;
+    int launches = 0;
+    sample_init_kernel<<<(P.M + 255) / 256, 256, 0, stream>>>(st, P.M); ++launches;
+    const int spans[4] = {128, 1024, 8192, 32768};
+    int covered = 0;
+    for (int r = 0; r < 4 && covered < a.limit; ++r) {
+        const int span = spans[r];
+        long long items = (long long)P.M * ((span + kTryThreads - 1) / kTryThreads);
+        int grid = (int)(items < (long long)sm_count * 16 ? items : (long long)sm_count * 16);
+        prefilter_kernel<<<grid, kTryThreads, 0, stream>>>(a, span); ++launches;
+        exact_kernel<<<sm_count * 4, 128, 0, stream>>>(a); ++launches;
+        advance_kernel<<<1, 1024, 0, stream>>>(st, span, a.limit); ++launches;
+        covered += span;
+    }
+    if (covered < a.limit) { tail_kernel<<<P.M < sm_count * 4 ? P.M : sm_count * 4, kTryThreads, 0, stream>>>(a); ++launches; }
+    emit_kernel<<<(P.M + 63) / 64, 64, 0, stream>>>(a, poses, cells, tries); ++launches;
+    return launches;
 }
 
 }  // namespace esacb200

@@ -48,12 +48,14 @@ template <int NV>
 __device__ __forceinline__ void all_reduce(double (&v)[NV], RefShared& sh, const RefineArgs& a, int grp, int cta,
                                            unsigned& epoch) {
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-#pragma unroll
-    for (int i = 0; i < NV; ++i) {
-        double x = v[i];
+    if (NV == 1) {
+        double x = v[0];
 #pragma unroll
         for (int o = 16; o; o >>= 1) x += __shfl_xor_sync(0xffffffffu, x, o);
-        if (lane == 0) sh.red[warp][i] = x;
+        if (lane == 0) sh.red[warp][0] = x;
+    } else {
+        const double x = warp_reduce_scatter<NV>(v);
+        if (lane < NV) sh.red[warp][lane] = x;
     }
     __syncthreads();
     if (tid < NV) {
@@ -86,8 +88,10 @@ __device__ __forceinline__ void all_reduce(double (&v)[NV], RefShared& sh, const
 }
 
 // J^T J, J^T r and cost of the reprojection residuals over the masked cells, pose (R, t) in shared memory.
+// Coordinates are taken relative to the plane centre c (t here is R*c + t of the true pose): the same least-squares
+// problem, but rotation updates pivot inside the scene, which keeps J^T J well conditioned for world-scale maps.
 __device__ __forceinline__ void lm_accumulate(const float* __restrict__ pl, const Problem& P, const double* R, const double* t,
-                                              const uint32_t* mask, int w0, int w1, double (&acc)[kRedN]) {
+                                              const double* c, const uint32_t* mask, int w0, int w1, double (&acc)[kRedN]) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 #pragma unroll
     for (int i = 0; i < kRedN; ++i) acc[i] = 0;
@@ -99,7 +103,7 @@ __device__ __forceinline__ void lm_accumulate(const float* __restrict__ pl, cons
         const int yy = p / P.W, xx = p - yy * P.W;
         const double px = (double)(xx * P.sub + P.sub / 2 - P.shiftX);
         const double py = (double)(yy * P.sub + P.sub / 2 - P.shiftY);
-        const double X = (double)pl[p], Y = (double)pl[P.N + p], Z = (double)pl[2 * (size_t)P.N + p];
+        const double X = (double)pl[p] - c[0], Y = (double)pl[P.N + p] - c[1], Z = (double)pl[2 * (size_t)P.N + p] - c[2];
         const double qx = R[0] * X + R[1] * Y + R[2] * Z;
         const double qy = R[3] * X + R[4] * Y + R[5] * Z;
         const double qz = R[6] * X + R[7] * Y + R[8] * Z;
@@ -144,6 +148,7 @@ __global__ void __launch_bounds__(kRefThreads, 1) refine_kernel(const __grid_con
         const int e = a.assign32[h];
         const float* pl = a.coords + (size_t)e * 3 * P.N;
         uint32_t* mbase = a.masks + (size_t)job * 2 * a.mask_words;
+        const double cen[3] = {(double)a.centres[e * 3], (double)a.centres[e * 3 + 1], (double)a.centres[e * 3 + 2]};
         Pose pose = a.poses_in[h];
         double best = 4;
         int rounds = 0, sel = 0;
@@ -175,11 +180,11 @@ __global__ void __launch_bounds__(kRefThreads, 1) refine_kernel(const __grid_con
             // ---- least-squares PnP on that set, started at the current pose ----
             if (tid == 0) {
                 for (int i = 0; i < 9; ++i) sh.R[i] = R0[i];
-                for (int i = 0; i < 3; ++i) sh.t[i] = pose.t[i];
+                for (int i = 0; i < 3; ++i) sh.t[i] = R0[i * 3] * cen[0] + R0[i * 3 + 1] * cen[1] + R0[i * 3 + 2] * cen[2] + pose.t[i];
             }
             __syncthreads();
             double acc[kRedN];
-            lm_accumulate(pl, P, sh.R, sh.t, mtent, w0, w1, acc);
+            lm_accumulate(pl, P, sh.R, sh.t, cen, mtent, w0, w1, acc);
             all_reduce<kRedN>(acc, sh, a, grp, cta, epoch);
             if (tid < kRedN) sh.cur[tid] = sh.tot[tid];
             if (tid == 0) sh.lambda = 1e-3;
@@ -222,7 +227,7 @@ __global__ void __launch_bounds__(kRefThreads, 1) refine_kernel(const __grid_con
                 __syncthreads();
                 const int flag = sh.flag;
                 if (flag == 0) { failed = true; break; }
-                lm_accumulate(pl, P, sh.Rc, sh.tc, mtent, w0, w1, acc);
+                lm_accumulate(pl, P, sh.Rc, sh.tc, cen, mtent, w0, w1, acc);
                 all_reduce<kRedN>(acc, sh, a, grp, cta, epoch);
                 const bool accept = sh.tot[27] <= sh.cur[27];   // false for NaN
                 const double lambda = sh.lambda;
@@ -246,7 +251,7 @@ __global__ void __launch_bounds__(kRefThreads, 1) refine_kernel(const __grid_con
             if (failed) break;  // "abort if PnP fails" (esac_util.h:426-437): previous pose and map stay
             Pose np_;
             rodrigues_m2v(sh.R, np_.r);
-            for (int i = 0; i < 3; ++i) np_.t[i] = sh.t[i];
+            for (int i = 0; i < 3; ++i) np_.t[i] = sh.t[i] - (sh.R[i * 3] * cen[0] + sh.R[i * 3 + 1] * cen[1] + sh.R[i * 3 + 2] * cen[2]);
             bool bad = false;
             for (int i = 0; i < 3; ++i) bad = bad || !(np_.r[i] == np_.r[i]) || !(np_.t[i] == np_.t[i]);
             __syncthreads();

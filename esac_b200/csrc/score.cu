@@ -135,10 +135,7 @@ __global__ void fold_kernel(const Pose* __restrict__ poses, const int* __restric
         A[r * 4 + 3] = (float)(sc * b);
     }
     PosePk pk;
-    for (int r = 0; r < 3; ++r) {
-        pk.v[r * 2 + 0] = make_float4(A[r * 4 + 0], A[r * 4 + 0], A[r * 4 + 1], A[r * 4 + 1]);
-        pk.v[r * 2 + 1] = make_float4(A[r * 4 + 2], A[r * 4 + 2], A[r * 4 + 3], A[r * 4 + 3]);
-    }
+    for (int r = 0; r < 3; ++r) pk.v[r] = make_float4(A[r * 4 + 0], A[r * 4 + 1], A[r * 4 + 2], A[r * 4 + 3]);
     out[s] = pk;
 }
 
@@ -165,8 +162,6 @@ __device__ __forceinline__ float mufu_rcp(float x) {
     asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
     return y;
 }
-__device__ __forceinline__ float2 lo2(const float4& v) { return make_float2(v.x, v.y); }
-__device__ __forceinline__ float2 hi2(const float4& v) { return make_float2(v.z, v.w); }
 
 template <int PPT, bool TAIL>
 __device__ __forceinline__ void score_item(const ScoreArgs& a, const ChunkDesc cd, const int tile, const float4* sPose,
@@ -232,15 +227,19 @@ __device__ __forceinline__ void score_item(const ScoreArgs& a, const ChunkDesc c
     const float2 one = make_float2(1.f, 1.f), tiny = make_float2(1e-30f, 1e-30f);
     const float mr = P.max_reproj;
 
-    for (int hl = 0; hl < cd.count; ++hl) {
-        const float4* q = sPose + hl * 6;
-        const float4 r0a = q[0], r0b = q[1], r1a = q[2], r1b = q[3], r2a = q[4], r2b = q[5];
+    // soft-inlier sum of this thread's PPT cells for hypothesis hl (pose = 3 x LDS.128, scalars broadcast to f32x2)
+    auto one_hyp = [&](int hl) -> float {
+        const float4* q = sPose + hl * 3;
+        const float4 r0 = q[0], r1 = q[1], r2 = q[2];
+        const float2 a00 = make_float2(r0.x, r0.x), a01 = make_float2(r0.y, r0.y), a02 = make_float2(r0.z, r0.z), b0 = make_float2(r0.w, r0.w);
+        const float2 a10 = make_float2(r1.x, r1.x), a11 = make_float2(r1.y, r1.y), a12 = make_float2(r1.z, r1.z), b1 = make_float2(r1.w, r1.w);
+        const float2 a20 = make_float2(r2.x, r2.x), a21 = make_float2(r2.y, r2.y), a22 = make_float2(r2.z, r2.z), b2 = make_float2(r2.w, r2.w);
         float2 acc = make_float2(0.f, 0.f);
 #pragma unroll
         for (int j = 0; j < NP; ++j) {
-            float2 xc = __ffma2_rn(lo2(r0a), X[j], __ffma2_rn(hi2(r0a), Y[j], __ffma2_rn(lo2(r0b), Z[j], hi2(r0b))));
-            float2 yc = __ffma2_rn(lo2(r1a), X[j], __ffma2_rn(hi2(r1a), Y[j], __ffma2_rn(lo2(r1b), Z[j], hi2(r1b))));
-            float2 zc = __ffma2_rn(lo2(r2a), X[j], __ffma2_rn(hi2(r2a), Y[j], __ffma2_rn(lo2(r2b), Z[j], hi2(r2b))));
+            float2 xc = __ffma2_rn(a00, X[j], __ffma2_rn(a01, Y[j], __ffma2_rn(a02, Z[j], b0)));
+            float2 yc = __ffma2_rn(a10, X[j], __ffma2_rn(a11, Y[j], __ffma2_rn(a12, Z[j], b1)));
+            float2 zc = __ffma2_rn(a20, X[j], __ffma2_rn(a21, Y[j], __ffma2_rn(a22, Z[j], b2)));
             float2 pu = __ffma2_rn(A[j], zc, xc);
             float2 pv = __ffma2_rn(B[j], zc, yc);
             float2 num = __ffma2_rn(pu, pu, __fmul2_rn(pv, pv));
@@ -256,7 +255,29 @@ __device__ __forceinline__ void score_item(const ScoreArgs& a, const ChunkDesc c
             if (TAIL) acc = __ffma2_rn(w, V[j], acc);
             else acc = __fadd2_rn(acc, w);
         }
-        float s = acc.x + acc.y;
+        return acc.x + acc.y;
+    };
+
+    int hl = 0;
+    // four hypotheses per iteration: a transposing butterfly leaves the warp totals of hypotheses hl..hl+3 on
+    // lanes 0 / 8 / 16 / 24 with 6 shuffles instead of 20
+    for (; hl + 4 <= cd.count; hl += 4) {
+        const float v0 = one_hyp(hl), v1 = one_hyp(hl + 1), v2 = one_hyp(hl + 2), v3 = one_hyp(hl + 3);
+        const bool hi16 = lane & 16, hi8 = lane & 8;
+        float k0_ = hi16 ? v2 : v0, k1_ = hi16 ? v3 : v1;   // kept
+        float s0_ = hi16 ? v0 : v2, s1_ = hi16 ? v1 : v3;   // sent
+        k0_ += __shfl_xor_sync(0xffffffffu, s0_, 16);
+        k1_ += __shfl_xor_sync(0xffffffffu, s1_, 16);
+        float c = hi8 ? k1_ : k0_;
+        const float d = hi8 ? k0_ : k1_;
+        c += __shfl_xor_sync(0xffffffffu, d, 8);
+        c += __shfl_xor_sync(0xffffffffu, c, 4);
+        c += __shfl_xor_sync(0xffffffffu, c, 2);
+        c += __shfl_xor_sync(0xffffffffu, c, 1);
+        if ((lane & 7) == 0) sWarp[warp][hl + (lane >> 3)] = c;
+    }
+    for (; hl < cd.count; ++hl) {
+        float s = one_hyp(hl);
 #pragma unroll
         for (int o = 16; o; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
         if (lane == 0) sWarp[warp][hl] = s;
@@ -272,7 +293,7 @@ __device__ __forceinline__ void score_item(const ScoreArgs& a, const ChunkDesc c
 
 template <int PPT>
 __global__ void __launch_bounds__(kScoreThreads, 2) score_kernel(const __grid_constant__ ScoreArgs a) {
-    __shared__ float4 sPose[kMaxChunk * 6];
+    __shared__ float4 sPose[kMaxChunk * 3];
     __shared__ float sWarp[kScoreThreads / 32][kMaxChunk];
     __shared__ int sItem;
     constexpr int TP = kScoreThreads * PPT;
@@ -288,7 +309,7 @@ __global__ void __launch_bounds__(kScoreThreads, 2) score_kernel(const __grid_co
         const int chunk = item / a.T, tile = item - chunk * a.T;
         const ChunkDesc cd = a.chunks[chunk];
         const float4* src = (const float4*)(a.poses + cd.slot0);
-        for (int i = tid; i < cd.count * 6; i += kScoreThreads) sPose[i] = src[i];
+        for (int i = tid; i < cd.count * 3; i += kScoreThreads) sPose[i] = src[i];
         __syncthreads();
         if (ragged && tile == a.T - 1) score_item<PPT, true>(a, cd, tile, sPose, sWarp);
         else score_item<PPT, false>(a, cd, tile, sPose, sWarp);
