@@ -208,14 +208,23 @@ template <> struct Num<double> {
     static ESAC_HD double cos_(double v) { return cos(v); }
     static ESAC_HD double cbrt_(double v) { return cbrt(v); }
     static ESAC_HD double abs_(double v) { return fabs(v); }
+    static ESAC_HD double div_(double a, double b) { return a / b; }
     static constexpr double kRelTiny = 1e-14;   // "this coefficient is zero" threshold
     static constexpr double kDiscTol = 1e-13;   // slightly negative discriminants are clamped to 0
     static constexpr double kUncertain = 0.0;   // no uncertainty band in double
 };
 template <> struct Num<float> {
+#ifdef __CUDA_ARCH__
+    // the float path only feeds a conservative prefilter: MUFU-based approximations are enough
+    static ESAC_HD float sqrt_(float v) { float r; asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(v)); return r; }
+    static ESAC_HD float cos_(float v) { return __cosf(v); }
+    static ESAC_HD float div_(float a, float b) { return __fdividef(a, b); }
+#else
     static ESAC_HD float sqrt_(float v) { return sqrtf(v); }
-    static ESAC_HD float acos_(float v) { return acosf(v); }
     static ESAC_HD float cos_(float v) { return cosf(v); }
+    static ESAC_HD float div_(float a, float b) { return a / b; }
+#endif
+    static ESAC_HD float acos_(float v) { return acosf(v); }
     static ESAC_HD float cbrt_(float v) { return cbrtf(v); }
     static ESAC_HD float abs_(float v) { return fabsf(v); }
     static constexpr float kRelTiny = 1e-6f;
@@ -365,32 +374,34 @@ ESAC_HD int real_cubic_roots(T c3, T c2, T c1, T c0, T roots[3]) {
     if (!(scale > 0)) return 0;
     if (N::abs_(c3) < N::kRelTiny * scale) {  // quadratic (the root at infinity is handled by the caller)
         if (N::abs_(c2) < N::kRelTiny * scale) {
-            if (N::abs_(c1) > 0) roots[n++] = -c0 / c1;
+            if (N::abs_(c1) > 0) roots[n++] = N::div_(-c0, c1);
             return n;
         }
         T disc = c1 * c1 - 4 * c2 * c0;
         if (disc < 0) return 0;
         T sq = N::sqrt_(disc);
         T q = T(-0.5) * (c1 + (c1 >= 0 ? sq : -sq));
-        roots[n++] = q / c2;
-        if (q != 0) roots[n++] = c0 / q;
+        roots[n++] = N::div_(q, c2);
+        if (q != 0) roots[n++] = N::div_(c0, q);
         return n;
     }
-    T a = c2 / c3, b = c1 / c3, c = c0 / c3;
-    T Q = (a * a - 3 * b) / 9, Rr = (2 * a * a * a - 9 * a * b + 27 * c) / 54;
+    const T ic3 = N::div_(T(1), c3);
+    T a = c2 * ic3, b = c1 * ic3, c = c0 * ic3;
+    T Q = (a * a - 3 * b) * T(1.0 / 9.0), Rr = (2 * a * a * a - 9 * a * b + 27 * c) * T(1.0 / 54.0);
     T Q3 = Q * Q * Q;
     if (Rr * Rr < Q3) {
-        T th = N::acos_(Rr / N::sqrt_(Q3));
+        T th = N::acos_(N::div_(Rr, N::sqrt_(Q3)));
         T sq = -2 * N::sqrt_(Q);
         const T twopi = T(2 * 3.14159265358979323846);
-        roots[0] = sq * N::cos_(th / 3) - a / 3;
-        roots[1] = sq * N::cos_((th + twopi) / 3) - a / 3;
-        roots[2] = sq * N::cos_((th - twopi) / 3) - a / 3;
+        const T third = T(1.0 / 3.0);
+        roots[0] = sq * N::cos_(th * third) - a * third;
+        roots[1] = sq * N::cos_((th + twopi) * third) - a * third;
+        roots[2] = sq * N::cos_((th - twopi) * third) - a * third;
         n = 3;
     } else {
         T A = -(Rr >= 0 ? T(1) : T(-1)) * N::cbrt_(N::abs_(Rr) + N::sqrt_(Rr * Rr - Q3));
-        T B = A != 0 ? Q / A : 0;
-        roots[0] = A + B - a / 3;
+        T B = A != 0 ? N::div_(Q, A) : 0;
+        roots[0] = A + B - a * T(1.0 / 3.0);
         n = 1;
     }
     for (int i = 0; i < n; ++i) {  // Newton polish on the monic cubic
@@ -399,7 +410,7 @@ ESAC_HD int real_cubic_roots(T c3, T c2, T c1, T c0, T roots[3]) {
             T fv = ((g + a) * g + b) * g + c;
             T dv = (3 * g + 2 * a) * g + b;
             if (!(N::abs_(dv) > 0)) break;
-            g -= fv / dv;
+            g -= N::div_(fv, dv);
         }
         roots[i] = g;
     }
@@ -416,8 +427,9 @@ ESAC_HD int line_conic(const T l[3], const T D[9], T sol[][3], int n, bool& unce
     if (!(N::abs_(l[k]) > 0)) return n;
     int i = (k + 1) % 3, j = (k + 2) % 3;
     T u[3] = {0, 0, 0}, v[3] = {0, 0, 0};
-    u[i] = 1; u[k] = -l[i] / l[k];
-    v[j] = 1; v[k] = -l[j] / l[k];
+    const T ilk = N::div_(T(1), l[k]);
+    u[i] = 1; u[k] = -l[i] * ilk;
+    v[j] = 1; v[k] = -l[j] * ilk;
     T A = quad3(D, u, u), B = quad3(D, u, v), C = quad3(D, v, v);
     T disc = B * B - A * C;
     T mag = B * B + N::abs_(A * C);
@@ -428,14 +440,14 @@ ESAC_HD int line_conic(const T l[3], const T D[9], T sol[][3], int n, bool& unce
     T q = -(B + (B >= 0 ? sq : -sq));
     if (N::abs_(A) >= N::abs_(C)) {
         if (!(N::abs_(A) > 0)) return n;
-        T a1 = q / A, a2 = (q != 0) ? C / q : a1;  // alpha = (-B +- sq)/A, beta = 1 (stable form)
+        T a1 = N::div_(q, A), a2 = (q != 0) ? N::div_(C, q) : a1;  // alpha = (-B +- sq)/A, beta = 1 (stable form)
         for (int s = 0; s < 2; ++s) {
             T al = s == 0 ? a1 : a2;
             for (int c = 0; c < 3; ++c) sol[n][c] = al * u[c] + v[c];
             ++n;
         }
     } else {
-        T b1 = q / C, b2 = (q != 0) ? A / q : b1;
+        T b1 = N::div_(q, C), b2 = (q != 0) ? N::div_(A, q) : b1;
         for (int s = 0; s < 2; ++s) {
             T be = s == 0 ? b1 : b2;
             for (int c = 0; c < 3; ++c) sol[n][c] = u[c] + be * v[c];
@@ -515,7 +527,8 @@ ESAC_HD int p3p_lambdas(const T y[3][3], const T x[3][3], T lam[4][3], T& amax, 
     T c12 = y[0][0] * y[1][0] + y[0][1] * y[1][1] + y[0][2] * y[1][2];
     T c13 = y[0][0] * y[2][0] + y[0][1] * y[2][1] + y[0][2] * y[2][2];
     T c23 = y[1][0] * y[2][0] + y[1][1] * y[2][1] + y[1][2] * y[2][2];
-    T s12 = a12 / amax, s13 = a13 / amax, s23 = a23 / amax;
+    const T iamax = N::div_(T(1), amax);
+    T s12 = a12 * iamax, s13 = a13 * iamax, s23 = a23 * iamax;
     if (N::kUncertain > 0) {  // float prefilter: needle triangles / nearly parallel bearings are left to the exact path
         const T cm = N::abs_(c12) > N::abs_(c13) ? (N::abs_(c12) > N::abs_(c23) ? N::abs_(c12) : N::abs_(c23))
                                                  : (N::abs_(c13) > N::abs_(c23) ? N::abs_(c13) : N::abs_(c23));
@@ -547,7 +560,7 @@ ESAC_HD int p3p_lambdas(const T y[3][3], const T x[3][3], T lam[4][3], T& amax, 
                 for (int i = 0; i < 9; ++i) D0[i] = D1[i] + g * D2[i];
                 Dother = D2;
             } else {
-                T ig = 1 / g;
+                T ig = N::div_(T(1), g);
                 for (int i = 0; i < 9; ++i) D0[i] = ig * D1[i] + D2[i];
                 Dother = D1;
             }
@@ -572,7 +585,8 @@ ESAC_HD int p3p_lambdas(const T y[3][3], const T x[3][3], T lam[4][3], T& amax, 
             continue;
         }
         T sq = N::sqrt_(-bii);
-        T p[3] = {B[i] / sq, B[3 + i] / sq, B[6 + i] / sq};
+        const T isq = N::div_(T(1), sq);
+        T p[3] = {B[i] * isq, B[3 + i] * isq, B[6 + i] * isq};
         T C[9] = {D0[0], D0[1] - p[2], D0[2] + p[1], D0[3] + p[2], D0[4], D0[5] - p[0],
                   D0[6] - p[1], D0[7] + p[0], D0[8]};
         int rm = 0, cm = 0;
@@ -593,9 +607,9 @@ ESAC_HD int p3p_lambdas(const T y[3][3], const T x[3][3], T lam[4][3], T& amax, 
         T q13 = l0 * l0 + l2 * l2 - 2 * c13 * l0 * l2;
         T q23 = l1 * l1 + l2 * l2 - 2 * c23 * l1 * l2;
         T sc;  // fix the scale with the largest quadratic form
-        if (q12 >= q13 && q12 >= q23) sc = s12 / q12;
-        else if (q13 >= q23) sc = s13 / q13;
-        else sc = s23 / q23;
+        if (q12 >= q13 && q12 >= q23) sc = N::div_(s12, q12);
+        else if (q13 >= q23) sc = N::div_(s13, q13);
+        else sc = N::div_(s23, q23);
         if (!(sc > 0) || !(sc < T(1e30))) continue;
         sc = N::sqrt_(sc);
         T mx = N::abs_(l0) > N::abs_(l1) ? N::abs_(l0) : N::abs_(l1);
@@ -716,19 +730,37 @@ ESAC_HD bool p3p_may_pass(const float obj[4][3], const float img[4][2], float f,
     bool unc;
     int n = p3p_lambdas<float>(y, x, lam, amax, cs, ss, unc);
     if (unc || !(amax == amax)) return true;
+    if (n == 0) return false;
+    // 4th point in the (non-orthogonal) frame of the scene triangle: x3 = x0 + al*d1 + be*d2 + ga*(d1 x d2).
+    // A rigid motion maps that frame onto the camera-side triangle's, so no rotation has to be built per root.
+    const float* d1 = x[1];
+    const float* d2 = x[2];  // x[0] is the origin after recentring
+    float nrm[3];
+    cross3(d1, d2, nrm);
+    const float g11 = d1[0] * d1[0] + d1[1] * d1[1] + d1[2] * d1[2], g12 = d1[0] * d2[0] + d1[1] * d2[1] + d1[2] * d2[2];
+    const float g22 = d2[0] * d2[0] + d2[1] * d2[1] + d2[2] * d2[2], nn = nrm[0] * nrm[0] + nrm[1] * nrm[1] + nrm[2] * nrm[2];
+    const float det = g11 * g22 - g12 * g12;
+    if (!(det > 1e-6f * g11 * g22) || !(nn > 0.f)) return true;  // nearly collinear scene triangle: exact path decides
+    const float v1 = x3[0] * d1[0] + x3[1] * d1[1] + x3[2] * d1[2], v2 = x3[0] * d2[0] + x3[1] * d2[1] + x3[2] * d2[2];
+    const float idet = Num<float>::div_(1.f, det);
+    const float al = (v1 * g22 - v2 * g12) * idet, be = (v2 * g11 - v1 * g12) * idet;
+    const float ga = Num<float>::div_(x3[0] * nrm[0] + x3[1] * nrm[1] + x3[2] * nrm[2], nn);
     const float lim = margin * tau, lim2 = lim * lim;
-    const float sa = sqrtf(amax);
+    const float sa = Num<float>::sqrt_(amax);
     for (int s = 0; s < n; ++s) {
-        float P[3][3], R[9], t[3];
-        for (int i = 0; i < 3; ++i)
-            for (int c = 0; c < 3; ++c) P[i][c] = lam[s][i] * sa * y[i][c];
-        if (!align_triangles<float>(P, x, R, t)) return true;
-        float xc = R[0] * x3[0] + R[1] * x3[1] + R[2] * x3[2] + t[0];
-        float yc = R[3] * x3[0] + R[4] * x3[1] + R[5] * x3[2] + t[1];
-        float zc = R[6] * x3[0] + R[7] * x3[1] + R[8] * x3[2] + t[2];
-        float iz = 1.f / zc;
-        float du = ppx + f * xc * iz - img[3][0], dv = ppy + f * yc * iz - img[3][1];
-        float e = du * du + dv * dv;
+        float P0[3], e1[3], e2[3], m[3];
+        for (int c = 0; c < 3; ++c) {
+            P0[c] = lam[s][0] * sa * y[0][c];
+            e1[c] = lam[s][1] * sa * y[1][c] - P0[c];
+            e2[c] = lam[s][2] * sa * y[2][c] - P0[c];
+        }
+        cross3(e1, e2, m);
+        const float xc = P0[0] + al * e1[0] + be * e2[0] + ga * m[0];
+        const float yc = P0[1] + al * e1[1] + be * e2[1] + ga * m[1];
+        const float zc = P0[2] + al * e1[2] + be * e2[2] + ga * m[2];
+        const float iz = Num<float>::div_(1.f, zc);
+        const float du = ppx + f * xc * iz - img[3][0], dv = ppy + f * yc * iz - img[3][1];
+        const float e = du * du + dv * dv;
         if (!(e > lim2)) return true;  // close enough (or NaN/inf): let the exact path decide
     }
     return false;

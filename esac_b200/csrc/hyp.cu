@@ -6,7 +6,9 @@
 // try the sequential loop would have stopped at.  Wrong experts need ~1/P(4th point lands within tau) ~ 1e3 tries
 // per hypothesis, which makes this the most expensive stage of a step; it runs as waves of small kernels:
 //
-//   wave r (try window [base_h, base_h + span_r) of every unresolved hypothesis, span = 128, 1024, 8192, 32768):
+//   wave r (try window [base_h, base_h + span_r) of every unresolved hypothesis; span_0 = 128, then chosen on the
+//   device from the acceptance rate seen so far, ~1.25 / p, so that ~70% of the remaining hypotheses resolve per
+//   wave and < 2x the necessary tries are evaluated):
 //     prefilter_kernel   one thread per try, fp32 only: p3p_may_pass() discards tries whose every P3P root misses
 //                        the 4th point by > 4 tau (>95% on wrong experts); survivors are appended to a global list
 //     exact_kernel       one thread per survivor: the fp64 path (p3p_pose + minimal_set_gate) whose verdict is the
@@ -66,12 +68,13 @@ __device__ __noinline__ bool exact_try(const SampleArgs& a, int h, int t, Pose& 
 __global__ void sample_init_kernel(SampleState st, int M) {
     const int h = blockIdx.x * blockDim.x + threadIdx.x;
     if (h < M) { st.best[h] = kNoTry; st.base[h] = 0; st.ovf[h] = kNoTry; st.list[h] = h; }
-    if (h == 0) { st.counters[0] = M; st.counters[1] = 0; st.counters[2] = 0; }  // n_unresolved, n_survivors, next-list fill
+    if (h == 0) { st.counters[0] = M; st.counters[1] = 0; st.counters[2] = 0; st.counters[3] = 128; }  // unresolved, survivors, -, span
 }
 
 // ---- wave phase 1: fp32 prefilter, one thread per try --------------------------------------------------------
-__global__ void __launch_bounds__(kTryThreads) prefilter_kernel(const __grid_constant__ SampleArgs a, int span) {
+__global__ void __launch_bounds__(kTryThreads) prefilter_kernel(const __grid_constant__ SampleArgs a) {
     const int n_unres = a.st.counters[0];
+    const int span = a.st.counters[3];
     const int cph = (span + kTryThreads - 1) / kTryThreads;  // chunks per hypothesis
     const long long n_items = (long long)n_unres * cph;
     const int lane = threadIdx.x & 31;
@@ -117,8 +120,9 @@ __global__ void __launch_bounds__(128) exact_kernel(const __grid_constant__ Samp
 }
 
 // ---- wave phase 3: bookkeeping ------------------------------------------------------------------------------
-__global__ void __launch_bounds__(1024) advance_kernel(SampleState st, int span, int limit) {
+__global__ void __launch_bounds__(1024) advance_kernel(SampleState st, int limit) {
     __shared__ int s_fill;
+    const int span = st.counters[3];
     if (threadIdx.x == 0) s_fill = 0;
     __syncthreads();
     const int n_unres = st.counters[0];
@@ -140,7 +144,16 @@ __global__ void __launch_bounds__(1024) advance_kernel(SampleState st, int span,
     const int nn = s_fill;
     for (int u = threadIdx.x; u < nn; u += blockDim.x) st.list[u] = next[u];
     __syncthreads();
-    if (threadIdx.x == 0) { st.counters[0] = nn; st.counters[1] = 0; }
+    if (threadIdx.x == 0) {
+        // next window: ~1.25 / (acceptance rate per try seen in this wave), a multiple of the CTA size
+        const double tried = (double)n_unres * (double)span;
+        const double hits = n_unres - nn > 0 ? (double)(n_unres - nn) : 0.5;
+        double next_span = 1.25 * tried / hits;
+        next_span = next_span < 128. ? 128. : (next_span > 65536. ? 65536. : next_span);
+        st.counters[3] = ((int)next_span + kTryThreads - 1) / kTryThreads * kTryThreads;
+        st.counters[0] = nn;
+        st.counters[1] = 0;
+    }
 }
 
 // ---- tail: CTA per unresolved hypothesis, both phases inside the CTA, up to the try limit --------------------
@@ -204,17 +217,14 @@ int launch_sample(const float* coords, const int* assign32, const Problem& P, ui
     a.injected = injected; a.inj_T = inj_T; a.st = st;
     int launches = 0;
     sample_init_kernel<<<(P.M + 255) / 256, 256, 0, stream>>>(st, P.M); ++launches;
-    const int spans[4] = {128, 1024, 8192, 32768};
-    int covered = 0;
-    for (int r = 0; r < 4 && covered < a.limit; ++r) {
-        const int span = spans[r];
-        long long items = (long long)P.M * ((span + kTryThreads - 1) / kTryThreads);
-        int grid = (int)(items < (long long)sm_count * 16 ? items : (long long)sm_count * 16);
-        prefilter_kernel<<<grid, kTryThreads, 0, stream>>>(a, span); ++launches;
+    const int kWaves = 7;
+    const int grid = sm_count * 16;
+    for (int r = 0; r < kWaves; ++r) {
+        prefilter_kernel<<<grid, kTryThreads, 0, stream>>>(a); ++launches;
         exact_kernel<<<sm_count * 4, 128, 0, stream>>>(a); ++launches;
-        advance_kernel<<<1, 1024, 0, stream>>>(st, span, a.limit); ++launches;
-        covered += span;
+        advance_kernel<<<1, 1024, 0, stream>>>(st, a.limit); ++launches;
     }
+    const int covered = 0;
     if (covered < a.limit) { tail_kernel<<<P.M < sm_count * 4 ? P.M : sm_count * 4, kTryThreads, 0, stream>>>(a); ++launches; }
     emit_kernel<<<(P.M + 63) / 64, 64, 0, stream>>>(a, poses, cells, tries); ++launches;
     return launches;

@@ -8,9 +8,14 @@
 // * The inlier test reproduces getReproErrs' arithmetic exactly (fp64 transform, float-rounded
 //   projection, float difference, double norm -> float, clamp, `< tau`), because which cells pass is
 //   what makes two implementations agree or not.
-// * The least-squares solve is Levenberg-Marquardt on the local rotation parametrisation
-//   R <- exp([w]x) R (no Rodrigues Jacobian per point); it is run to convergence (1e-12), so the
-//   minimiser -- which does not depend on the parametrisation -- is what is handed back as (rvec, tvec).
+// * The least-squares solve reproduces OpenCV's own iteration (cvFindExtrinsicCameraParams2 + CvLevMarq as
+//   observed on cv2 4.13: parameters (rvec, tvec), J^T J with its diagonal scaled by 1 + 10^k, k from -3,
+//   step accepted when the error norm does not grow, at most 20 iterations, stop when the relative parameter
+//   change drops below FLT_EPSILON).  This matters: on world-scale maps (|t| ~ 1e3) that criterion stops long
+//   before the minimiser, so only the same iteration gives the same pose and the same next inlier set.
+//   Per cell the Jacobian is taken in a cheap, well-conditioned local frame (rotation increment about the
+//   plane centre); the reduced 6x6 sums are then mapped to the (rvec, tvec) frame by one 6x6 change of
+//   variables per evaluation.
 // * A job (one hypothesis) is worked on by a group of `group` CTAs; reductions over cells go
 //   warp shuffle -> shared memory -> (if group > 1) per-CTA slots in global memory + a counting
 //   barrier, every CTA summing the slots in the same order so all take identical decisions.
@@ -30,11 +35,11 @@ struct RefShared {
     double tot[kRedN];
     double R[9];
     double t[3];
-    double Rc[9];
-    double tc[3];
-    double cur[kRedN];
-    double lambda;
-    int flag;
+    double cur[kRedN];   // (rvec, tvec)-frame sums at the last accepted parameters
+    double cand[kRedN];  // same at the candidate
+    double par[6], prev[6];
+    double prev_err, err_norm;
+    int lamlg, iters, flag;
 };
 
 __device__ __forceinline__ unsigned ld_acquire(const unsigned* p) {
@@ -125,11 +130,6 @@ __device__ __forceinline__ void lm_accumulate(const float* __restrict__ pl, cons
     }
 }
 
-__device__ __forceinline__ void mat3mul(const double* A, const double* B, double* C) {
-    for (int r = 0; r < 3; ++r)
-        for (int c = 0; c < 3; ++c) C[r * 3 + c] = A[r * 3] * B[c] + A[r * 3 + 1] * B[3 + c] + A[r * 3 + 2] * B[6 + c];
-}
-
 __global__ void __launch_bounds__(kRefThreads, 1) refine_kernel(const __grid_constant__ RefineArgs a) {
     __shared__ RefShared sh;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -177,81 +177,130 @@ __global__ void __launch_bounds__(kRefThreads, 1) refine_kernel(const __grid_con
             __syncthreads();
             if (!(n_in > best)) break;  // converged (esac_util.h:417-418)
             best = n_in;
-            // ---- least-squares PnP on that set, started at the current pose ----
-            if (tid == 0) {
-                for (int i = 0; i < 9; ++i) sh.R[i] = R0[i];
-                for (int i = 0; i < 3; ++i) sh.t[i] = R0[i * 3] * cen[0] + R0[i * 3 + 1] * cen[1] + R0[i * 3 + 2] * cen[2] + pose.t[i];
-            }
-            __syncthreads();
-            double acc[kRedN];
-            lm_accumulate(pl, P, sh.R, sh.t, cen, mtent, w0, w1, acc);
-            all_reduce<kRedN>(acc, sh, a, grp, cta, epoch);
-            if (tid < kRedN) sh.cur[tid] = sh.tot[tid];
-            if (tid == 0) sh.lambda = 1e-3;
-            __syncthreads();
-            bool failed = false;
-            for (int it = 0; it < 60; ++it) {
-                // thread 0 solves the damped normal equations and publishes the candidate
+            // ---- solvePnP(SOLVEPNP_ITERATIVE, useExtrinsicGuess) on that set, started at the current pose ----
+            // evaluate(): sums of the cell Jacobians / residuals at sh.par, mapped to the (rvec, tvec) frame -> sh.cand
+            auto evaluate = [&]() {
+                double G[36];  // d(local increment) / d(rvec, tvec), thread 0 only
                 if (tid == 0) {
-                    double H[36], g[6], d[6];
-                    const double* cur = sh.cur;
-                    double lambda = sh.lambda;
+                    double R[9], dR[27];
+                    rodrigues_v2m(sh.par, R, dR);
+                    double Rc[3];
+                    for (int i = 0; i < 3; ++i) {
+                        Rc[i] = R[i * 3] * cen[0] + R[i * 3 + 1] * cen[1] + R[i * 3 + 2] * cen[2];
+                        sh.t[i] = Rc[i] + sh.par[3 + i];
+                    }
+                    for (int i = 0; i < 9; ++i) sh.R[i] = R[i];
+                    // T[:, i] = vee((dR/dr_i) R^T): rotation increment per unit rvec change
+                    double T[9];
+                    for (int i = 0; i < 3; ++i) {
+                        const double* d = dR + i * 9;
+                        double S21 = d[6] * R[3] + d[7] * R[4] + d[8] * R[5];  // (dR R^T)[2][1]
+                        double S02 = d[0] * R[6] + d[1] * R[7] + d[2] * R[8];  // [0][2]
+                        double S10 = d[3] * R[0] + d[4] * R[1] + d[5] * R[2];  // [1][0]
+                        T[0 * 3 + i] = S21; T[1 * 3 + i] = S02; T[2 * 3 + i] = S10;
+                    }
+                    // local (w', t') = Q (w, t), Q = [[I, 0], [-[Rc]x, I]];  (w, t) = P (r, t), P = blkdiag(T, I)
+                    const double K[9] = {0, Rc[2], -Rc[1], -Rc[2], 0, Rc[0], Rc[1], -Rc[0], 0};  // -[Rc]x
+                    for (int i = 0; i < 36; ++i) G[i] = 0;
+                    for (int r = 0; r < 3; ++r)
+                        for (int c = 0; c < 3; ++c) {
+                            G[r * 6 + c] = T[r * 3 + c];
+                            double kt = 0;
+                            for (int k = 0; k < 3; ++k) kt += K[r * 3 + k] * T[k * 3 + c];
+                            G[(3 + r) * 6 + c] = kt;
+                        }
+                    for (int r = 0; r < 3; ++r) G[(3 + r) * 6 + 3 + r] = 1;
+                }
+                __syncthreads();
+                double acc[kRedN];
+                lm_accumulate(pl, P, sh.R, sh.t, cen, mtent, w0, w1, acc);
+                all_reduce<kRedN>(acc, sh, a, grp, cta, epoch);
+                if (tid == 0) {
+                    double Hl[36], H1[36];
                     int k = 0;
                     for (int i = 0; i < 6; ++i)
-                        for (int j = i; j < 6; ++j) { H[i * 6 + j] = cur[k]; H[j * 6 + i] = cur[k]; ++k; }
-                    for (int i = 0; i < 6; ++i) g[i] = -cur[21 + i];
-                    int ok = 0;
-                    for (int tr = 0; tr < 40 && !ok; ++tr) {
-                        double Hd[36];
-                        for (int i = 0; i < 36; ++i) Hd[i] = H[i];
-                        for (int i = 0; i < 6; ++i) Hd[i * 6 + i] = H[i * 6 + i] * (1. + lambda);
-                        ok = chol_solve6(Hd, g, d) ? 1 : 0;
-                        if (!ok) lambda *= 10.;
+                        for (int j = i; j < 6; ++j) { Hl[i * 6 + j] = sh.tot[k]; Hl[j * 6 + i] = sh.tot[k]; ++k; }
+                    for (int i = 0; i < 6; ++i)
+                        for (int j = 0; j < 6; ++j) {
+                            double v = 0;
+                            for (int q = 0; q < 6; ++q) v += Hl[i * 6 + q] * G[q * 6 + j];
+                            H1[i * 6 + j] = v;
+                        }
+                    k = 0;
+                    for (int i = 0; i < 6; ++i)
+                        for (int j = i; j < 6; ++j) {
+                            double v = 0;
+                            for (int q = 0; q < 6; ++q) v += G[q * 6 + i] * H1[q * 6 + j];
+                            sh.cand[k++] = v;
+                        }
+                    for (int i = 0; i < 6; ++i) {
+                        double v = 0;
+                        for (int q = 0; q < 6; ++q) v += G[q * 6 + i] * sh.tot[21 + q];
+                        sh.cand[21 + i] = v;
                     }
-                    bool fin = ok;
-                    for (int i = 0; i < 6; ++i) fin = fin && (d[i] == d[i]) && fabs(d[i]) < 1e300;
-                    if (fin) {
-                        double dR[9];
-                        rodrigues_v2m(d, dR, nullptr);
-                        mat3mul(dR, sh.R, sh.Rc);
-                        for (int i = 0; i < 3; ++i) sh.tc[i] = sh.t[i] + d[3 + i];
-                        double sw = fmax(fabs(d[0]), fmax(fabs(d[1]), fabs(d[2])));
-                        double st = fmax(fabs(d[3]), fmax(fabs(d[4]), fabs(d[5])));
-                        double tn = fmax(fabs(sh.t[0]), fmax(fabs(sh.t[1]), fabs(sh.t[2])));
-                        sh.flag = (sw < 1e-12 && st < 1e-12 * (1. + tn)) ? 2 : 1;
-                    } else {
-                        sh.flag = 0;
-                    }
-                    sh.lambda = lambda;
+                    sh.cand[27] = sh.tot[27];
                 }
                 __syncthreads();
-                const int flag = sh.flag;
-                if (flag == 0) { failed = true; break; }
-                lm_accumulate(pl, P, sh.Rc, sh.tc, cen, mtent, w0, w1, acc);
-                all_reduce<kRedN>(acc, sh, a, grp, cta, epoch);
-                const bool accept = sh.tot[27] <= sh.cur[27];   // false for NaN
-                const double lambda = sh.lambda;
-                __syncthreads();
-                if (accept) {
-                    if (tid < kRedN) sh.cur[tid] = sh.tot[tid];
-                    if (tid == 32) {
-                        for (int i = 0; i < 9; ++i) sh.R[i] = sh.Rc[i];
-                        for (int i = 0; i < 3; ++i) sh.t[i] = sh.tc[i];
-                        sh.lambda = fmax(lambda * 0.1, 1e-15);
-                    }
-                    __syncthreads();
-                    if (flag == 2) break;
-                } else {
-                    if (flag == 2) break;  // step below resolution and no decrease: at the minimum
-                    if (tid == 0) sh.lambda = lambda * 10.;
-                    __syncthreads();
-                    if (lambda * 10. > 1e12) break;
+            };
+            // step(): param = prevParam - solve(JtJ with diag * (1 + 10^lamlg), JtErr)   (CvLevMarq::step)
+            auto lm_step = [&]() {
+                double A[36], Ai[36];
+                int k = 0;
+                for (int i = 0; i < 6; ++i)
+                    for (int j = i; j < 6; ++j) { A[i * 6 + j] = sh.cur[k]; A[j * 6 + i] = sh.cur[k]; ++k; }
+                const double lambda = exp((double)sh.lamlg * log(10.));
+                for (int i = 0; i < 6; ++i) A[i * 6 + i] *= 1. + lambda;
+                pinv_sym6(A, Ai);  // solve(..., DECOMP_SVD)
+                for (int i = 0; i < 6; ++i) {
+                    double d = 0;
+                    for (int j = 0; j < 6; ++j) d += Ai[i * 6 + j] * sh.cur[21 + j];
+                    sh.par[i] = sh.prev[i] - d;
                 }
+            };
+            if (tid == 0) {
+                for (int i = 0; i < 3; ++i) { sh.par[i] = pose.r[i]; sh.par[3 + i] = pose.t[i]; }
+                sh.lamlg = -3;
+                sh.iters = 0;
             }
-            if (failed) break;  // "abort if PnP fails" (esac_util.h:426-437): previous pose and map stay
+            __syncthreads();
+            evaluate();
+            if (tid == 0) {
+                for (int i = 0; i < kRedN; ++i) sh.cur[i] = sh.cand[i];
+                sh.prev_err = sqrt(sh.cand[27]);  // iters == 0: prevErrNorm = ||err(param0)||
+            }
+            __syncthreads();
+            for (int outer = 0; outer < 20; ++outer) {
+                if (tid == 0) {
+                    for (int i = 0; i < 6; ++i) sh.prev[i] = sh.par[i];
+                    lm_step();
+                }
+                __syncthreads();
+                for (;;) {  // CHECK_ERR (the evaluation also yields the Jacobian sums reused if the step is kept)
+                    evaluate();
+                    if (tid == 0) {
+                        sh.err_norm = sqrt(sh.cand[27]);
+                        if (sh.err_norm > sh.prev_err && ++sh.lamlg <= 16) { lm_step(); sh.flag = 1; }
+                        else sh.flag = 0;
+                    }
+                    __syncthreads();
+                    if (sh.flag == 0) break;
+                }
+                if (tid == 0) {
+                    sh.lamlg = sh.lamlg - 1 > -16 ? sh.lamlg - 1 : -16;
+                    double dn = 0, pn = 0;
+                    for (int i = 0; i < 6; ++i) { const double d = sh.par[i] - sh.prev[i]; dn += d * d; pn += sh.prev[i] * sh.prev[i]; }
+                    const bool done = (++sh.iters >= 20) || (sqrt(dn) / sqrt(pn) < (double)FLT_EPSILON);
+                    sh.flag = done ? 1 : 0;
+                    if (!done) {
+                        sh.prev_err = sh.err_norm;
+                        for (int i = 0; i < kRedN; ++i) sh.cur[i] = sh.cand[i];
+                    }
+                }
+                __syncthreads();
+                if (sh.flag) break;
+            }
             Pose np_;
-            rodrigues_m2v(sh.R, np_.r);
-            for (int i = 0; i < 3; ++i) np_.t[i] = sh.t[i] - (sh.R[i * 3] * cen[0] + sh.R[i * 3 + 1] * cen[1] + sh.R[i * 3 + 2] * cen[2]);
+            for (int i = 0; i < 3; ++i) { np_.r[i] = sh.par[i]; np_.t[i] = sh.par[3 + i]; }
             bool bad = false;
             for (int i = 0; i < 3; ++i) bad = bad || !(np_.r[i] == np_.r[i]) || !(np_.t[i] == np_.t[i]);
             __syncthreads();
