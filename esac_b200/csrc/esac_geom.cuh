@@ -404,6 +404,7 @@ ESAC_HD int real_cubic_roots(T c3, T c2, T c1, T c0, T roots[3]) {
         roots[0] = A + B - a * T(1.0 / 3.0);
         n = 1;
     }
+#pragma unroll 1
     for (int i = 0; i < n; ++i) {  // Newton polish on the monic cubic
         T g = roots[i];
         for (int it = 0; it < 4; ++it) {
@@ -418,8 +419,9 @@ ESAC_HD int real_cubic_roots(T c3, T c2, T c1, T c0, T roots[3]) {
 }
 
 // Intersect the line {lam : l.lam = 0} with the conic lam^T D lam = 0; appends direction vectors.
+// (kept out of line: three call sites, and the sampling prefilter is instruction-cache bound)
 template <typename T>
-ESAC_HD int line_conic(const T l[3], const T D[9], T sol[][3], int n, bool& uncertain) {
+ESAC_HDN int line_conic(const T l[3], const T D[9], T sol[][3], int n, bool& uncertain) {
     using N = Num<T>;
     int k = 0;
     if (N::abs_(l[1]) > N::abs_(l[k])) k = 1;
@@ -548,6 +550,7 @@ ESAC_HD int p3p_lambdas(const T y[3][3], const T x[3][3], T lam[4][3], T& amax, 
     bool inf_root = N::abs_(k3) < N::kRelTiny * kscale;
     T dirs[8][3];
     int nd = 0;
+#pragma unroll 1
     for (int ri = 0; ri < nr + (inf_root ? 1 : 0) && nd == 0; ++ri) {
         T D0[9];
         const T* Dother;
@@ -601,6 +604,7 @@ ESAC_HD int p3p_lambdas(const T y[3][3], const T x[3][3], T lam[4][3], T& amax, 
         nd = line_conic(m, Dother, dirs, nd, uncertain);
     }
     int ns = 0;
+#pragma unroll 1
     for (int d = 0; d < nd && ns < 4; ++d) {
         T l0 = dirs[d][0], l1 = dirs[d][1], l2 = dirs[d][2];
         T q12 = l0 * l0 + l1 * l1 - 2 * c12 * l0 * l1;
@@ -747,6 +751,7 @@ ESAC_HD bool p3p_may_pass(const float obj[4][3], const float img[4][2], float f,
     const float ga = Num<float>::div_(x3[0] * nrm[0] + x3[1] * nrm[1] + x3[2] * nrm[2], nn);
     const float lim = margin * tau, lim2 = lim * lim;
     const float sa = Num<float>::sqrt_(amax);
+#pragma unroll 1
     for (int s = 0; s < n; ++s) {
         float P0[3], e1[3], e2[3], m[3];
         for (int c = 0; c < 3; ++c) {

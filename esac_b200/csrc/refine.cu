@@ -82,10 +82,14 @@ __device__ __forceinline__ void all_reduce(double (&v)[NV], RefShared& sh, const
             while (ld_acquire(&a.barrier[grp]) < target) { }
         }
         __syncthreads();
-        if (tid < NV) {
+        // every CTA sums the group's slots in the same fixed order: warp w owns values w, w + 16; its lanes stride
+        // over the CTAs (independent L2 reads in flight), then a shuffle tree
+        for (int v_ = warp; v_ < NV; v_ += kRefWarps) {
             double s = 0;
-            for (int c = 0; c < a.group; ++c) s += __ldcg(&slots[((size_t)c * 2 + buf) * kSlot + tid]);
-            sh.tot[tid] = s;
+            for (int c = lane; c < a.group; c += 32) s += __ldcg(&slots[((size_t)c * 2 + buf) * kSlot + v_]);
+#pragma unroll
+            for (int o = 16; o; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+            if (lane == 0) sh.tot[v_] = s;
         }
         __syncthreads();
         ++epoch;
@@ -250,12 +254,18 @@ __global__ void __launch_bounds__(kRefThreads, 1) refine_kernel(const __grid_con
                     for (int j = i; j < 6; ++j) { A[i * 6 + j] = sh.cur[k]; A[j * 6 + i] = sh.cur[k]; ++k; }
                 const double lambda = exp((double)sh.lamlg * log(10.));
                 for (int i = 0; i < 6; ++i) A[i * 6 + i] *= 1. + lambda;
-                pinv_sym6(A, Ai);  // solve(..., DECOMP_SVD)
-                for (int i = 0; i < 6; ++i) {
-                    double d = 0;
-                    for (int j = 0; j < 6; ++j) d += Ai[i * 6 + j] * sh.cur[21 + j];
-                    sh.par[i] = sh.prev[i] - d;
+                // solve(JtJN, JtErr, DECOMP_SVD): Cholesky when the damped matrix is positive definite (the solution is
+                // the same up to rounding, which the iteration is insensitive to), SVD-style pseudo-inverse otherwise
+                double dlt[6];
+                if (!chol_solve6(A, &sh.cur[21], dlt)) {
+                    pinv_sym6(A, Ai);
+                    for (int i = 0; i < 6; ++i) {
+                        double d = 0;
+                        for (int j = 0; j < 6; ++j) d += Ai[i * 6 + j] * sh.cur[21 + j];
+                        dlt[i] = d;
+                    }
                 }
+                for (int i = 0; i < 6; ++i) sh.par[i] = sh.prev[i] - dlt[i];
             };
             if (tid == 0) {
                 for (int i = 0; i < 3; ++i) { sh.par[i] = pose.r[i]; sh.par[3 + i] = pose.t[i]; }
