@@ -121,7 +121,7 @@ def run_reference(args, rank: int, world: int):
     if rank != 0:
         return
     cores = os.cpu_count() or 1
-    take = max(2 * cores, 32)
+    take = max(cores, 32)
     take = min(take, E_PER_GPU * HYPS_PER_EXPERT)
     from esac_b200.synth import make_scene
     sc = make_scene(E=E_PER_GPU, H=H, W=W, M=HYPS_PER_EXPERT, sub=SUB, seed=0, per_expert=True, active_only=False)
@@ -263,7 +263,7 @@ def main():
                 "score_launch": {"ppt": last["score_ppt"], "grid": last["score_grid"], "refine_group": last["refine_group"]}}
         if world == 1 and not args.no_cpu_baseline:
             cores = os.cpu_count() or 1
-            take = min(max(2 * cores, 32), M_local)
+            take = min(max(cores, 32), M_local)
             sc = scenes[0]
             idx = np.linspace(0, M_local - 1, take).astype(int)
             from copy import copy

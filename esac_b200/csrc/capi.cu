@@ -212,11 +212,15 @@ int stage_inputs(esacb200_ctx* ctx, Plan& pl, const float* coords, const int64_t
 int run_sample(esacb200_ctx* ctx, const Plan& pl, uint64_t seed) {
     const Problem& P = pl.P;
     const int cap = 1 << 20;
-    CK(ctx->smp_int.ensure(((size_t)P.M * 5 + 8) * 4));
-    CK(ctx->smp_surv.ensure((size_t)cap * sizeof(int2)));
+    const int cap_acc = 1 << 16;
+    CK(ctx->smp_int.ensure(((size_t)P.M * 6 + 8) * 4 + 8));
+    CK(ctx->smp_surv.ensure((size_t)cap * sizeof(int2) + (size_t)cap_acc * sizeof(Accepted)));
     SampleState st;
-    int* b = ctx->smp_int.as<int>();
-    st.best = b; st.base = b + P.M; st.ovf = b + 2 * (size_t)P.M; st.list = b + 3 * (size_t)P.M; st.counters = b + 5 * (size_t)P.M;
+    st.best = ctx->smp_int.as<unsigned long long>();  // 8-byte aligned: first in the buffer
+    int* b = ctx->smp_int.as<int>() + 2 * (size_t)P.M;
+    st.base = b; st.ovf = b + P.M; st.list = b + 2 * (size_t)P.M; st.counters = b + 4 * (size_t)P.M;
+    st.stage = (Accepted*)((char*)ctx->smp_surv.p + (size_t)cap * sizeof(int2));
+    st.cap_acc = cap_acc;
     st.surv = ctx->smp_surv.as<int2>();
     st.cap = cap;
     st.M = P.M;

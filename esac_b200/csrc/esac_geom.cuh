@@ -651,7 +651,7 @@ ESAC_HDN int p3p_solve(const double y[3][3], const double x[3][3], double Rs[4][
                            lam[0] * lam[0] + lam[2] * lam[2] - 2 * c13 * lam[0] * lam[2] - s13,
                            lam[1] * lam[1] + lam[2] * lam[2] - 2 * c23 * lam[1] * lam[2] - s23};
             res = fabs(r[0]) + fabs(r[1]) + fabs(r[2]);
-            if (it == 5) break;
+            if (it == 5 || res < 1e-15) break;  // quadratic convergence: usually two iterations
             double Jm[9] = {2 * lam[0] - 2 * c12 * lam[1], 2 * lam[1] - 2 * c12 * lam[0], 0,
                             2 * lam[0] - 2 * c13 * lam[2], 0, 2 * lam[2] - 2 * c13 * lam[0],
                             0, 2 * lam[1] - 2 * c23 * lam[2], 2 * lam[2] - 2 * c23 * lam[1]};

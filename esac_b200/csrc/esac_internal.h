@@ -88,14 +88,20 @@ void launch_select(const float* part, const int* slot_of, const Problem& P, int 
 
 // --- hyp.cu -------------------------------------------------------------------------------
 // Work state of the sampling waves (all device memory, M = hypotheses).
+struct Accepted {
+    Pose pose;
+    int cells[8];
+};
 struct SampleState {
-    int* best;      // [M] lowest accepted try (0x7fffffff = none yet)
+    unsigned long long* best;  // [M] (lowest accepted try << 32) | staging slot; ~0 = none yet
+    Accepted* stage;           // [cap_acc] poses of accepted tries
+    int cap_acc;
     int* base;      // [M] first try not judged yet
     int* ovf;       // [M] lowest survivor that did not fit the list in the current wave
     int* list;      // [2M] unresolved hypotheses (second half: scratch for rebuilding)
     int2* surv;     // [cap] (hypothesis, try) pairs that passed the float prefilter
     int cap;
-    int* counters;  // [0] unresolved, [1] survivors
+    int* counters;  // [0] unresolved, [1] survivors, [2] staged accepts, [3] span of the current wave
     int M;
 };
 // Returns the number of kernel launches it enqueued.

@@ -27,6 +27,8 @@ namespace esacb200 {
 
 constexpr int kTryThreads = 128;
 constexpr int kNoTry = 0x7fffffff;
+constexpr unsigned long long kNoKey = ~0ull;   // best[h]: (try << 32) | staging slot
+constexpr unsigned kNoSlot = 0xffffffffu;
 
 struct SampleArgs {
     const float* coords;
@@ -67,7 +69,7 @@ __device__ __noinline__ bool exact_try(const SampleArgs& a, int h, int t, Pose& 
 // state init: every hypothesis unresolved, window at try 0
 __global__ void sample_init_kernel(SampleState st, int M) {
     const int h = blockIdx.x * blockDim.x + threadIdx.x;
-    if (h < M) { st.best[h] = kNoTry; st.base[h] = 0; st.ovf[h] = kNoTry; st.list[h] = h; }
+    if (h < M) { st.best[h] = kNoKey; st.base[h] = 0; st.ovf[h] = kNoTry; st.list[h] = h; }
     if (h == 0) { st.counters[0] = M; st.counters[1] = 0; st.counters[2] = 0; st.counters[3] = 128; }  // unresolved, survivors, -, span
 }
 
@@ -115,7 +117,18 @@ __global__ void __launch_bounds__(128) exact_kernel(const __grid_constant__ Samp
         Pose pose;
         int cx[4], cy[4];
         bool solved;
-        if (exact_try(a, ht.x, ht.y, pose, cx, cy, solved)) atomicMin(&a.st.best[ht.x], ht.y);
+        if (exact_try(a, ht.x, ht.y, pose, cx, cy, solved)) {
+            // stage the accepted pose so that emit_kernel does not have to solve it again
+            unsigned slot = (unsigned)atomicAdd(&a.st.counters[2], 1);
+            if (slot < (unsigned)a.st.cap_acc) {
+                Accepted& ac = a.st.stage[slot];
+                ac.pose = pose;
+                for (int j = 0; j < 4; ++j) { ac.cells[2 * j] = cx[j]; ac.cells[2 * j + 1] = cy[j]; }
+            } else {
+                slot = kNoSlot;
+            }
+            atomicMin(&a.st.best[ht.x], ((unsigned long long)(unsigned)ht.y << 32) | slot);
+        }
     }
 }
 
@@ -132,9 +145,9 @@ __global__ void __launch_bounds__(1024) advance_kernel(SampleState st, int limit
         const int h = st.list[u];
         const int ovf = st.ovf[h];
         const int end = min(st.base[h] + span, ovf);  // tries below `end` have all been judged
-        const bool resolved = st.best[h] < end;
+        const bool resolved = (long long)(st.best[h] >> 32) < (long long)end;
         if (!resolved) {
-            if (st.best[h] != kNoTry) st.best[h] = kNoTry;  // an accept beyond an overflow hole does not count yet
+            if (st.best[h] != kNoKey) st.best[h] = kNoKey;  // an accept beyond an overflow hole does not count yet
             st.base[h] = end;
             st.ovf[h] = kNoTry;
             if (end < limit) next[atomicAdd(&s_fill, 1)] = h;
@@ -188,7 +201,7 @@ __global__ void __launch_bounds__(kTryThreads) tail_kernel(const __grid_constant
             if (s_best != kNoTry) break;
             base += span;
         }
-        if (threadIdx.x == 0 && s_best != kNoTry) a.st.best[h] = s_best;
+        if (threadIdx.x == 0 && s_best != kNoTry) a.st.best[h] = ((unsigned long long)(unsigned)s_best << 32) | kNoSlot;
     }
 }
 
@@ -196,13 +209,20 @@ __global__ void __launch_bounds__(kTryThreads) tail_kernel(const __grid_constant
 __global__ void __launch_bounds__(64) emit_kernel(const __grid_constant__ SampleArgs a, Pose* poses, int* cells, int* tries) {
     const int h = blockIdx.x * blockDim.x + threadIdx.x;
     if (h >= a.P.M) return;
-    const int b = a.st.best[h];
-    const int t = b != kNoTry ? b : a.limit - 1;  // exhausted: the state of the last try survives (esac_util.h:154-224)
+    const unsigned long long key = a.st.best[h];
+    const int t = key != kNoKey ? (int)(key >> 32) : a.limit - 1;  // exhausted: the state of the last try survives (esac_util.h:154-224)
+    const unsigned slot = (unsigned)(key & 0xffffffffu);
     Pose pose;
     int cx[4], cy[4];
-    bool solved;
-    exact_try(a, h, t, pose, cx, cy, solved);
-    if (!solved) { for (int c = 0; c < 3; ++c) { pose.r[c] = 0; pose.t[c] = 0; } }  // safeSolvePnP failure state
+    if (key != kNoKey && slot != kNoSlot) {
+        const Accepted& ac = a.st.stage[slot];
+        pose = ac.pose;
+        for (int j = 0; j < 4; ++j) { cx[j] = ac.cells[2 * j]; cy[j] = ac.cells[2 * j + 1]; }
+    } else {
+        bool solved;
+        exact_try(a, h, t, pose, cx, cy, solved);
+        if (!solved) { for (int c = 0; c < 3; ++c) { pose.r[c] = 0; pose.t[c] = 0; } }  // safeSolvePnP failure state
+    }
     poses[h] = pose;
     for (int j = 0; j < 4; ++j) { cells[h * 8 + 2 * j] = cx[j]; cells[h * 8 + 2 * j + 1] = cy[j]; }
     tries[h] = t + 1;

@@ -31,8 +31,8 @@ constexpr int kRedN = 28;   // 21 (J^T J upper) + 6 (J^T r) + 1 (cost)
 constexpr int kSlot = 32;   // doubles per CTA slot
 
 struct RefShared {
-    double red[kRefWarps][kRedN];
-    double tot[kRedN];
+    double red[kRefWarps][32];
+    double tot[32];
     double R[9];
     double t[3];
     double cur[kRedN];   // (rvec, tvec)-frame sums at the last accepted parameters
@@ -99,20 +99,39 @@ __device__ __forceinline__ void all_reduce(double (&v)[NV], RefShared& sh, const
 // J^T J, J^T r and cost of the reprojection residuals over the masked cells, pose (R, t) in shared memory.
 // Coordinates are taken relative to the plane centre c (t here is R*c + t of the true pose): the same least-squares
 // problem, but rotation updates pivot inside the scene, which keeps J^T J well conditioned for world-scale maps.
+// BUILD_MASK: the pass also decides, for every cell, whether it is an inlier of the true pose (R0, t0) -- exactly
+// getReproErrs' arithmetic --, writes the bit mask and counts (acc[28]); otherwise the mask is read.
+template <bool BUILD_MASK>
 __device__ __forceinline__ void lm_accumulate(const float* __restrict__ pl, const Problem& P, const double* R, const double* t,
-                                              const double* c, const uint32_t* mask, int w0, int w1, double (&acc)[kRedN]) {
+                                              const double* c, uint32_t* mask, int w0, int w1, const double* R0, const double* t0,
+                                              double (&acc)[kRedN + 1]) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 #pragma unroll
-    for (int i = 0; i < kRedN; ++i) acc[i] = 0;
+    for (int i = 0; i < kRedN + 1; ++i) acc[i] = 0;
     const double f = (double)P.f, cx = (double)P.ppx, cy = (double)P.ppy;
     for (int w = w0 + warp; w < w1; w += kRefWarps) {
-        const uint32_t bits = mask[w];
-        if (!((bits >> lane) & 1u)) continue;
         const int p = w * 32 + lane;
         const int yy = p / P.W, xx = p - yy * P.W;
-        const double px = (double)(xx * P.sub + P.sub / 2 - P.shiftX);
-        const double py = (double)(yy * P.sub + P.sub / 2 - P.shiftY);
-        const double X = (double)pl[p] - c[0], Y = (double)pl[P.N + p] - c[1], Z = (double)pl[2 * (size_t)P.N + p] - c[2];
+        const int ipx = xx * P.sub + P.sub / 2 - P.shiftX, ipy = yy * P.sub + P.sub / 2 - P.shiftY;
+        float Xf = 0.f, Yf = 0.f, Zf = 0.f;
+        bool inl;
+        if (BUILD_MASK) {
+            inl = false;
+            if (p < P.N) {
+                Xf = pl[p]; Yf = pl[P.N + p]; Zf = pl[2 * (size_t)P.N + p];
+                float err = repro_err_f(R0, t0, f, cx, cy, Xf, Yf, Zf, (float)ipx, (float)ipy);
+                err = (P.max_reproj < err) ? P.max_reproj : err;  // std::min(err, maxReproj): NaN stays NaN
+                inl = err < P.tau;                                  // esac_util.h:406
+            }
+            const uint32_t bits = __ballot_sync(0xffffffffu, inl);
+            if (lane == 0) { mask[w] = bits; acc[kRedN] += (double)__popc(bits); }
+        } else {
+            inl = (mask[w] >> lane) & 1u;
+            if (inl) { Xf = pl[p]; Yf = pl[P.N + p]; Zf = pl[2 * (size_t)P.N + p]; }
+        }
+        if (!inl) continue;
+        const double px = (double)ipx, py = (double)ipy;
+        const double X = (double)Xf - c[0], Y = (double)Yf - c[1], Z = (double)Zf - c[2];
         const double qx = R[0] * X + R[1] * Y + R[2] * Z;
         const double qy = R[3] * X + R[4] * Y + R[5] * Z;
         const double qz = R[6] * X + R[7] * Y + R[8] * Z;
@@ -157,33 +176,13 @@ __global__ void __launch_bounds__(kRefThreads, 1) refine_kernel(const __grid_con
         double best = 4;
         int rounds = 0, sel = 0;
         for (int step = 0; step < a.max_ref_steps; ++step) {
-            // ---- inliers of the current pose (esac_util.h:403-415) ----
+            // ---- inliers of the current pose (esac_util.h:403-415), fused with the first Jacobian evaluation ----
             double R0[9];
             rodrigues_v2m(pose.r, R0, nullptr);
             uint32_t* mtent = mbase + (size_t)(1 - sel) * a.mask_words;
-            double cnt[1] = {0};
-            for (int w = w0 + warp; w < w1; w += kRefWarps) {
-                const int p = w * 32 + lane;
-                bool inl = false;
-                if (p < P.N) {
-                    const int yy = p / P.W, xx = p - yy * P.W;
-                    const float px = (float)(xx * P.sub + P.sub / 2 - P.shiftX);
-                    const float py = (float)(yy * P.sub + P.sub / 2 - P.shiftY);
-                    float err = repro_err_f(R0, pose.t, f, cx, cy, pl[p], pl[P.N + p], pl[2 * (size_t)P.N + p], px, py);
-                    err = (P.max_reproj < err) ? P.max_reproj : err;  // std::min(err, maxReproj): NaN stays NaN
-                    inl = err < P.tau;
-                }
-                const uint32_t bits = __ballot_sync(0xffffffffu, inl);
-                if (lane == 0) { mtent[w] = bits; cnt[0] += (double)__popc(bits); }
-            }
-            all_reduce<1>(cnt, sh, a, grp, cta, epoch);   // also publishes the mask words to the block
-            const double n_in = sh.tot[0];
-            __syncthreads();
-            if (!(n_in > best)) break;  // converged (esac_util.h:417-418)
-            best = n_in;
             // ---- solvePnP(SOLVEPNP_ITERATIVE, useExtrinsicGuess) on that set, started at the current pose ----
             // evaluate(): sums of the cell Jacobians / residuals at sh.par, mapped to the (rvec, tvec) frame -> sh.cand
-            auto evaluate = [&]() {
+            auto evaluate = [&](bool first) {
                 double G[36];  // d(local increment) / d(rvec, tvec), thread 0 only
                 if (tid == 0) {
                     double R[9], dR[27];
@@ -216,9 +215,10 @@ __global__ void __launch_bounds__(kRefThreads, 1) refine_kernel(const __grid_con
                     for (int r = 0; r < 3; ++r) G[(3 + r) * 6 + 3 + r] = 1;
                 }
                 __syncthreads();
-                double acc[kRedN];
-                lm_accumulate(pl, P, sh.R, sh.t, cen, mtent, w0, w1, acc);
-                all_reduce<kRedN>(acc, sh, a, grp, cta, epoch);
+                double acc[kRedN + 1];
+                if (first) lm_accumulate<true>(pl, P, sh.R, sh.t, cen, mtent, w0, w1, R0, pose.t, acc);
+                else lm_accumulate<false>(pl, P, sh.R, sh.t, cen, mtent, w0, w1, R0, pose.t, acc);
+                all_reduce<kRedN + 1>(acc, sh, a, grp, cta, epoch);
                 if (tid == 0) {
                     double Hl[36], H1[36];
                     int k = 0;
@@ -273,7 +273,11 @@ __global__ void __launch_bounds__(kRefThreads, 1) refine_kernel(const __grid_con
                 sh.iters = 0;
             }
             __syncthreads();
-            evaluate();
+            evaluate(true);
+            const double n_in = sh.tot[kRedN];
+            __syncthreads();
+            if (!(n_in > best)) break;  // converged (esac_util.h:417-418)
+            best = n_in;
             if (tid == 0) {
                 for (int i = 0; i < kRedN; ++i) sh.cur[i] = sh.cand[i];
                 sh.prev_err = sqrt(sh.cand[27]);  // iters == 0: prevErrNorm = ||err(param0)||
@@ -286,7 +290,7 @@ __global__ void __launch_bounds__(kRefThreads, 1) refine_kernel(const __grid_con
                 }
                 __syncthreads();
                 for (;;) {  // CHECK_ERR (the evaluation also yields the Jacobian sums reused if the step is kept)
-                    evaluate();
+                    evaluate(false);
                     if (tid == 0) {
                         sh.err_norm = sqrt(sh.cand[27]);
                         if (sh.err_norm > sh.prev_err && ++sh.lamlg <= 16) { lm_step(); sh.flag = 1; }
