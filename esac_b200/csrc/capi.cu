@@ -14,6 +14,7 @@
 #include "../../include/esac_b200.h"
 #include "../../include/esac_b200_testhooks.h"
 #include "esac_internal.h"
+#include "esac_p3p_fast.cuh"
 #include "esac_rng.cuh"
 
 using namespace esacb200;
@@ -58,6 +59,7 @@ struct esacb200_ctx {
     int max_ref_steps = 100;
     int fixed_seed = 0;
     int refine_group_opt = 0;
+    int sample_prefilter = 1;
     int refine_coresident = 0;
     char err[512] = {0};
     // workspace
@@ -225,7 +227,7 @@ int run_sample(esacb200_ctx* ctx, const Plan& pl, uint64_t seed) {
     st.cap = cap;
     st.M = P.M;
     ctx->st.kernel_launches += launch_sample(pl.d_coords, ctx->assign32.as<int>(), P, seed, ctx->max_tries,
-                                             ctx->inj_M ? ctx->inject.as<int>() : nullptr, ctx->inj_T, st, ctx->sm_count,
+                                             ctx->inj_M ? ctx->inject.as<int>() : nullptr, ctx->inj_T, st, ctx->sm_count, ctx->sample_prefilter,
                                              ctx->poses.as<Pose>(), ctx->cells.as<int>(), ctx->tries.as<int>(), ctx->stream);
     CK(cudaGetLastError());
     mark(ctx, EV_SAMPLE);
@@ -411,6 +413,7 @@ int esacb200_set_option(esacb200_ctx* ctx, const char* key, double v) {
     else if (!strcmp(key, "max_ref_steps")) ctx->max_ref_steps = v < 0 ? 0 : (int)v;
     else if (!strcmp(key, "fixed_seed")) ctx->fixed_seed = v != 0;
     else if (!strcmp(key, "refine_group")) ctx->refine_group_opt = (int)v;
+    else if (!strcmp(key, "sample_prefilter")) ctx->sample_prefilter = v != 0;
     else return fail(ctx, ESACB200_ERR_ARG, "unknown option '%s'", key);
     return ESACB200_OK;
 }
@@ -741,7 +744,7 @@ void esacb200_host_try(const float* obj12, const float* img8, float f, float ppx
         for (int c = 0; c < 3; ++c) obj[i][c] = obj12[i * 3 + c];
         for (int c = 0; c < 2; ++c) img[i][c] = img8[i * 2 + c];
     }
-    *may_pass = p3p_may_pass(obj, img, f, ppx, ppy, tau, margin) ? 1 : 0;
+    *may_pass = p3p_may_pass_fast(obj, img, f, ppx, ppy, tau, margin) ? 1 : 0;
     Pose p;
     bool ok = p3p_pose(obj, img, (double)f, (double)ppx, (double)ppy, p);
     *accept = (ok && minimal_set_gate(obj, img, p, (double)f, (double)ppx, (double)ppy, tau)) ? 1 : 0;

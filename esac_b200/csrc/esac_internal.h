@@ -106,8 +106,8 @@ struct SampleState {
 };
 // Returns the number of kernel launches it enqueued.
 int launch_sample(const float* coords, const int* assign32, const Problem& P, uint64_t seed, int max_tries,
-                  const int* injected, int inj_T, const SampleState& st, int sm_count, Pose* poses, int* cells, int* tries,
-                  cudaStream_t st_);
+                  const int* injected, int inj_T, const SampleState& st, int sm_count, int use_prefilter, Pose* poses, int* cells,
+                  int* tries, cudaStream_t st_);
 
 // --- refine.cu ----------------------------------------------------------------------------
 // Refines poses_in[jobs[j]] -> poses_out[jobs[j]] for j < *n_jobs (device scalar) or n_jobs_host.

@@ -21,6 +21,7 @@
 // Keeping the float and double paths in different kernels matters: fused, the kernel ran at 10% issue utilisation,
 // stalled on instruction fetch (profiles/r01b_sample_kernel_ncu.json).
 #include "esac_internal.h"
+#include "esac_p3p_fast.cuh"
 #include "esac_rng.cuh"
 
 namespace esacb200 {
@@ -38,6 +39,7 @@ struct SampleArgs {
     int limit;            // tries allowed per hypothesis
     const int* injected;  // [M][inj_T][4][2] or null
     int inj_T;
+    int use_prefilter;    // 0: every try goes to the exact path (self-check of the prefilter)
     SampleState st;
 };
 
@@ -91,7 +93,7 @@ __global__ void __launch_bounds__(kTryThreads) prefilter_kernel(const __grid_con
             int cx[4], cy[4];
             float obj[4][3], img[4][2];
             load_try(a, h, t, cx, cy, obj, img);
-            pass = p3p_may_pass(obj, img, a.P.f, a.P.ppx, a.P.ppy, a.P.tau);
+            pass = !a.use_prefilter || p3p_may_pass_fast(obj, img, a.P.f, a.P.ppx, a.P.ppy, a.P.tau);
         }
         // warp-aggregated append of the survivors
         const unsigned m = __ballot_sync(0xffffffffu, pass);
@@ -187,7 +189,7 @@ __global__ void __launch_bounds__(kTryThreads) tail_kernel(const __grid_constant
                 int cx[4], cy[4];
                 float obj[4][3], img[4][2];
                 load_try(a, h, t, cx, cy, obj, img);
-                if (p3p_may_pass(obj, img, a.P.f, a.P.ppx, a.P.ppy, a.P.tau)) s_list[atomicAdd(&s_n, 1)] = t;
+                if (!a.use_prefilter || p3p_may_pass_fast(obj, img, a.P.f, a.P.ppx, a.P.ppy, a.P.tau)) s_list[atomicAdd(&s_n, 1)] = t;
             }
             __syncthreads();
             const int n = s_n;
@@ -229,12 +231,12 @@ __global__ void __launch_bounds__(64) emit_kernel(const __grid_constant__ Sample
 }
 
 int launch_sample(const float* coords, const int* assign32, const Problem& P, uint64_t seed, int max_tries,
-                  const int* injected, int inj_T, const SampleState& st, int sm_count, Pose* poses, int* cells, int* tries,
-                  cudaStream_t stream) {
+                  const int* injected, int inj_T, const SampleState& st, int sm_count, int use_prefilter, Pose* poses, int* cells,
+                  int* tries, cudaStream_t stream) {
     SampleArgs a;
     a.coords = coords; a.assign32 = assign32; a.P = P; a.seed = seed;
     a.limit = injected ? (max_tries < inj_T ? max_tries : inj_T) : max_tries;
-    a.injected = injected; a.inj_T = inj_T; a.st = st;
+    a.injected = injected; a.inj_T = inj_T; a.st = st; a.use_prefilter = use_prefilter;
     int launches = 0;
     sample_init_kernel<<<(P.M + 255) / 256, 256, 0, stream>>>(st, P.M); ++launches;
     const int kWaves = 7;

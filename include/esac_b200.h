@@ -48,7 +48,8 @@ int esacb200_set_stream(esacb200_ctx* ctx, void* cuda_stream);
 int esacb200_set_seed(esacb200_ctx* ctx, uint64_t seed);
 /* Options: "max_tries" (esac.cpp:44 MAX_SAMPLING_TRIES, default 1000000), "max_ref_steps"
  * (esac.cpp:45 MAX_REF_STEPS, default 100), "fixed_seed" (1: do not advance the call counter),
- * "refine_group" (CTAs per refinement job, 0 = automatic). */
+ * "refine_group" (CTAs per refinement job, 0 = automatic), "sample_prefilter" (default 1; 0 sends every sampling
+ * try through the exact fp64 path -- the results must not change, only the time). */
 int esacb200_set_option(esacb200_ctx* ctx, const char* key, double value);
 /* Inject minimal sets instead of drawing them: cells int32 [M][T][4][2] (x, y), host pointer,
  * copied; T candidate sets per hypothesis tried in order.  NULL clears.  Applies to the next call. */

@@ -167,3 +167,23 @@ def test_bad_arguments_raise(api):
         api.forward(sc.coords, sc.assign.astype(np.int32), out, *sc.params)
     with pytest.raises(RuntimeError):
         api.forward(sc.coords, sc.assign + 5, out, *sc.params)  # expert index out of range
+
+
+@pytest.mark.parametrize("kw", [dict(E=4, H=60, W=80, M=256, sub=8, seed=41, active_only=False, per_expert=True),
+                                dict(E=2, H=120, W=160, M=128, sub=4, seed=42, outdoor=True, active_only=False, per_expert=True)])
+def test_sampling_prefilter_does_not_change_results(api, kw):
+    """The fp32 prefilter of the sampling waves may only drop tries the exact path rejects: with it switched off the
+    accepted minimal sets, try counts and poses must be identical (hard maps: wrong experts need ~1e3 tries)."""
+    sc = make_scene(**kw)
+    out = np.zeros((4, 4), np.float32)
+    res = []
+    for flag in (1, 0):
+        api.set_option("sample_prefilter", flag)
+        api.set_seed(7)
+        api.forward(sc.coords, sc.assign, out, *sc.params)
+        res.append(api.last_hypotheses())
+    api.set_option("sample_prefilter", 1)
+    assert res[0]["tries"].max() > 500          # the scene did need many tries
+    assert np.array_equal(res[0]["tries"], res[1]["tries"])
+    assert np.array_equal(res[0]["cells"], res[1]["cells"])
+    assert np.array_equal(res[0]["poses"], res[1]["poses"])
