@@ -60,6 +60,7 @@ struct esacb200_ctx {
     int fixed_seed = 0;
     int refine_group_opt = 0;
     int sample_prefilter = 1;
+    int score_ppt_opt = 0, score_hc_opt = 0;
     int refine_coresident = 0;
     char err[512] = {0};
     // workspace
@@ -174,6 +175,8 @@ int stage_inputs(esacb200_ctx* ctx, Plan& pl, const float* coords, const int64_t
     };
     if (items(8, 64) < want) { ppt = 4; hc = 32; }
     if (ppt == 4 && items(4, 32) < want) { ppt = 2; hc = 16; }
+    if (ctx->score_ppt_opt == 2 || ctx->score_ppt_opt == 4 || ctx->score_ppt_opt == 8) ppt = ctx->score_ppt_opt;
+    if (ctx->score_hc_opt > 0) hc = ctx->score_hc_opt < 64 ? ctx->score_hc_opt : 64;
     pl.ppt = ppt;
     pl.hc = hc;
     pl.T = (P.N + score_tile_pixels(ppt) - 1) / score_tile_pixels(ppt);
@@ -414,6 +417,8 @@ int esacb200_set_option(esacb200_ctx* ctx, const char* key, double v) {
     else if (!strcmp(key, "fixed_seed")) ctx->fixed_seed = v != 0;
     else if (!strcmp(key, "refine_group")) ctx->refine_group_opt = (int)v;
     else if (!strcmp(key, "sample_prefilter")) ctx->sample_prefilter = v != 0;
+    else if (!strcmp(key, "score_ppt")) ctx->score_ppt_opt = (int)v;   // 0 = automatic, else 2 / 4 / 8 cells per thread
+    else if (!strcmp(key, "score_hc")) ctx->score_hc_opt = (int)v;     // 0 = automatic, else hypotheses per chunk (<= 64)
     else return fail(ctx, ESACB200_ERR_ARG, "unknown option '%s'", key);
     return ESACB200_OK;
 }
