@@ -474,12 +474,14 @@ ESAC_HD bool tri_frame(const T p0[3], const T p1[3], const T p2[3], T F[9]) {
     T d2[3] = {p1[0] - p2[0], p1[1] - p2[1], p1[2] - p2[2]};
     T n1 = N::sqrt_(d1[0] * d1[0] + d1[1] * d1[1] + d1[2] * d1[2]);
     if (!(n1 > 0)) return false;
-    T e1[3] = {d1[0] / n1, d1[1] / n1, d1[2] / n1};
+    const T in1 = N::div_(T(1), n1);
+    T e1[3] = {d1[0] * in1, d1[1] * in1, d1[2] * in1};
     T e3[3];
     cross3(d1, d2, e3);
     T n3 = N::sqrt_(e3[0] * e3[0] + e3[1] * e3[1] + e3[2] * e3[2]);
     if (!(n3 > 0)) return false;
-    e3[0] /= n3; e3[1] /= n3; e3[2] /= n3;
+    const T in3 = N::div_(T(1), n3);
+    e3[0] *= in3; e3[1] *= in3; e3[2] *= in3;
     T e2[3];
     cross3(e3, e1, e2);
     for (int r = 0; r < 3; ++r) {
@@ -500,8 +502,8 @@ ESAC_HD bool align_triangles(const T P[3][3], const T x[3][3], T R[9], T t[3]) {
             R[r * 3 + c] = Fc[r * 3 + 0] * Fw[c * 3 + 0] + Fc[r * 3 + 1] * Fw[c * 3 + 1] + Fc[r * 3 + 2] * Fw[c * 3 + 2];
     T mc[3], mw[3];
     for (int c = 0; c < 3; ++c) {
-        mc[c] = (P[0][c] + P[1][c] + P[2][c]) / 3;
-        mw[c] = (x[0][c] + x[1][c] + x[2][c]) / 3;
+        mc[c] = (P[0][c] + P[1][c] + P[2][c]) * T(1.0 / 3.0);
+        mw[c] = (x[0][c] + x[1][c] + x[2][c]) * T(1.0 / 3.0);
     }
     for (int r = 0; r < 3; ++r) t[r] = mc[r] - (R[r * 3] * mw[0] + R[r * 3 + 1] * mw[1] + R[r * 3 + 2] * mw[2]);
     return true;
@@ -706,7 +708,8 @@ ESAC_HD bool p3p_pose(const float obj[4][3], const float img[4][2], double f, do
         double xc = Rs[s][0] * X + Rs[s][1] * Y + Rs[s][2] * Z + ts[s][0];
         double yc = Rs[s][3] * X + Rs[s][4] * Y + Rs[s][5] * Z + ts[s][1];
         double zc = Rs[s][6] * X + Rs[s][7] * Y + Rs[s][8] * Z + ts[s][2];
-        double u = ppx + f * xc / zc, v = ppy + f * yc / zc;
+        const double izc = 1. / zc;
+        double u = ppx + f * xc * izc, v = ppy + f * yc * izc;
         double e = (u - img[3][0]) * (u - img[3][0]) + (v - img[3][1]) * (v - img[3][1]);
         if (!(e == e)) e = 1e300;  // NaN sorts last
         if (s == 0 || e < beste) { beste = e; best = s; }

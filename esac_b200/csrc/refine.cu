@@ -38,6 +38,7 @@ struct RefShared {
     double cur[kRedN];   // (rvec, tvec)-frame sums at the last accepted parameters
     double cand[kRedN];  // same at the candidate
     double par[6], prev[6];
+    double Rc[3], dR[27], T[9], G[36], H1[36];
     double prev_err, err_norm;
     int lamlg, iters, flag;
 };
@@ -183,66 +184,98 @@ __global__ void __launch_bounds__(kRefThreads, 1) refine_kernel(const __grid_con
             // ---- solvePnP(SOLVEPNP_ITERATIVE, useExtrinsicGuess) on that set, started at the current pose ----
             // evaluate(): sums of the cell Jacobians / residuals at sh.par, mapped to the (rvec, tvec) frame -> sh.cand
             auto evaluate = [&](bool first) {
-                double G[36];  // d(local increment) / d(rvec, tvec), thread 0 only
                 if (tid == 0) {
-                    double R[9], dR[27];
-                    rodrigues_v2m(sh.par, R, dR);
-                    double Rc[3];
+                    double R[9];
+                    rodrigues_v2m(sh.par, R, nullptr);
                     for (int i = 0; i < 3; ++i) {
-                        Rc[i] = R[i * 3] * cen[0] + R[i * 3 + 1] * cen[1] + R[i * 3 + 2] * cen[2];
-                        sh.t[i] = Rc[i] + sh.par[3 + i];
+                        sh.Rc[i] = R[i * 3] * cen[0] + R[i * 3 + 1] * cen[1] + R[i * 3 + 2] * cen[2];
+                        sh.t[i] = sh.Rc[i] + sh.par[3 + i];
                     }
                     for (int i = 0; i < 9; ++i) sh.R[i] = R[i];
-                    // T[:, i] = vee((dR/dr_i) R^T): rotation increment per unit rvec change
-                    double T[9];
-                    for (int i = 0; i < 3; ++i) {
-                        const double* d = dR + i * 9;
-                        double S21 = d[6] * R[3] + d[7] * R[4] + d[8] * R[5];  // (dR R^T)[2][1]
-                        double S02 = d[0] * R[6] + d[1] * R[7] + d[2] * R[8];  // [0][2]
-                        double S10 = d[3] * R[0] + d[4] * R[1] + d[5] * R[2];  // [1][0]
-                        T[0 * 3 + i] = S21; T[1 * 3 + i] = S02; T[2 * 3 + i] = S10;
-                    }
-                    // local (w', t') = Q (w, t), Q = [[I, 0], [-[Rc]x, I]];  (w, t) = P (r, t), P = blkdiag(T, I)
-                    const double K[9] = {0, Rc[2], -Rc[1], -Rc[2], 0, Rc[0], Rc[1], -Rc[0], 0};  // -[Rc]x
-                    for (int i = 0; i < 36; ++i) G[i] = 0;
-                    for (int r = 0; r < 3; ++r)
-                        for (int c = 0; c < 3; ++c) {
-                            G[r * 6 + c] = T[r * 3 + c];
-                            double kt = 0;
-                            for (int k = 0; k < 3; ++k) kt += K[r * 3 + k] * T[k * 3 + c];
-                            G[(3 + r) * 6 + c] = kt;
-                        }
-                    for (int r = 0; r < 3; ++r) G[(3 + r) * 6 + 3 + r] = 1;
                 }
                 __syncthreads();
                 double acc[kRedN + 1];
                 if (first) lm_accumulate<true>(pl, P, sh.R, sh.t, cen, mtent, w0, w1, R0, pose.t, acc);
                 else lm_accumulate<false>(pl, P, sh.R, sh.t, cen, mtent, w0, w1, R0, pose.t, acc);
                 all_reduce<kRedN + 1>(acc, sh, a, grp, cta, epoch);
-                if (tid == 0) {
-                    double Hl[36], H1[36];
-                    int k = 0;
-                    for (int i = 0; i < 6; ++i)
-                        for (int j = i; j < 6; ++j) { Hl[i * 6 + j] = sh.tot[k]; Hl[j * 6 + i] = sh.tot[k]; ++k; }
-                    for (int i = 0; i < 6; ++i)
-                        for (int j = 0; j < 6; ++j) {
-                            double v = 0;
-                            for (int q = 0; q < 6; ++q) v += Hl[i * 6 + q] * G[q * 6 + j];
-                            H1[i * 6 + j] = v;
+                // Change of variables local frame -> (rvec, tvec), spread over the lanes of warp 0:
+                //   local (w', t') = Q (w, t), Q = [[I, 0], [-[Rc]x, I]];  (w, t) = P (r, t), P = blkdiag(T, I),
+                //   T[:, i] = vee((dR/dr_i) R^T);  G = Q P;  JtJ = G^T H G, JtErr = G^T g.
+                if (warp == 0) {
+                    const double rx0 = sh.par[0], ry0 = sh.par[1], rz0 = sh.par[2];
+                    const double theta = sqrt(rx0 * rx0 + ry0 * ry0 + rz0 * rz0);
+                    if (lane < 27) {  // dR[i*9 + e] = d R[e] / d r_i  (cv::Rodrigues' Jacobian, esac_geom.cuh)
+                        const int i = lane / 9, e = lane - 9 * i, ra = e / 3, cb = e - 3 * ra;
+                        auto eps3 = [](int p_, int q_, int r_) { return (double)((p_ - q_) * (q_ - r_) * (r_ - p_)) * 0.5; };
+                        double v;
+                        if (theta < DBL_EPSILON) {
+                            v = -eps3(ra, cb, i);
+                        } else {
+                            const double c = cos(theta), sn = sin(theta), c1 = 1. - c, it = 1. / theta;
+                            const double rr[3] = {rx0 * it, ry0 * it, rz0 * it};
+                            const double ri = rr[i];
+                            const double a0 = -sn * ri, a1 = (sn - 2 * c1 * it) * ri, a2 = c1 * it, a3 = (c - sn * it) * ri, a4 = sn * it;
+                            const double I_e = ra == cb ? 1. : 0.;
+                            const double rrt = rr[ra] * rr[cb];
+                            const double drrt = (ra == i ? rr[cb] : 0.) + (cb == i ? rr[ra] : 0.);
+                            double rxm = 0;  // [r]x entry (ra, cb) = -eps(ra, cb, k) r_k
+                            for (int k = 0; k < 3; ++k) rxm -= eps3(ra, cb, k) * rr[k];
+                            const double drx = -eps3(ra, cb, i);
+                            v = a0 * I_e + a1 * rrt + a2 * drrt + a3 * rxm + a4 * drx;
                         }
-                    k = 0;
-                    for (int i = 0; i < 6; ++i)
-                        for (int j = i; j < 6; ++j) {
-                            double v = 0;
-                            for (int q = 0; q < 6; ++q) v += G[q * 6 + i] * H1[q * 6 + j];
-                            sh.cand[k++] = v;
-                        }
-                    for (int i = 0; i < 6; ++i) {
-                        double v = 0;
-                        for (int q = 0; q < 6; ++q) v += G[q * 6 + i] * sh.tot[21 + q];
-                        sh.cand[21 + i] = v;
+                        sh.dR[lane] = v;
                     }
-                    sh.cand[27] = sh.tot[27];
+                    __syncwarp();
+                    if (lane < 9) {  // T[row][i]: rows (2,1), (0,2), (1,0) of (dR_i R^T)
+                        const int row = lane / 3, i = lane - 3 * row;
+                        const int p_ = row == 0 ? 2 : (row == 1 ? 0 : 1), q_ = row == 0 ? 1 : (row == 1 ? 2 : 0);
+                        const double* d = sh.dR + i * 9 + p_ * 3;
+                        sh.T[lane] = d[0] * sh.R[q_ * 3] + d[1] * sh.R[q_ * 3 + 1] + d[2] * sh.R[q_ * 3 + 2];
+                    }
+                    __syncwarp();
+                    for (int idx = lane; idx < 36; idx += 32) {
+                        const int row = idx / 6, col = idx - 6 * row;
+                        double v = 0;
+                        if (row < 3) {
+                            v = col < 3 ? sh.T[row * 3 + col] : 0.;
+                        } else if (col < 3) {
+                            const int r = row - 3;  // -[Rc]x row r
+                            const double K0 = r == 0 ? 0. : (r == 1 ? -sh.Rc[2] : sh.Rc[1]);
+                            const double K1 = r == 0 ? sh.Rc[2] : (r == 1 ? 0. : -sh.Rc[0]);
+                            const double K2 = r == 0 ? -sh.Rc[1] : (r == 1 ? sh.Rc[0] : 0.);
+                            v = K0 * sh.T[col] + K1 * sh.T[3 + col] + K2 * sh.T[6 + col];
+                        } else {
+                            v = (col - 3 == row - 3) ? 1. : 0.;
+                        }
+                        sh.G[idx] = v;
+                    }
+                    __syncwarp();
+                    auto sym = [&](int i, int j) {  // upper-triangle storage of the reduced local J^T J
+                        const int lo = i < j ? i : j, hi = i < j ? j : i;
+                        return sh.tot[lo * 6 - lo * (lo - 1) / 2 + (hi - lo)];
+                    };
+                    for (int idx = lane; idx < 36; idx += 32) {
+                        const int i = idx / 6, j = idx - 6 * i;
+                        double v = 0;
+                        for (int q = 0; q < 6; ++q) v += sym(i, q) * sh.G[q * 6 + j];
+                        sh.H1[idx] = v;
+                    }
+                    __syncwarp();
+                    if (lane < 21) {
+                        int i = 0, rem = lane;
+                        while (rem >= 6 - i) { rem -= 6 - i; ++i; }
+                        const int j = i + rem;
+                        double v = 0;
+                        for (int q = 0; q < 6; ++q) v += sh.G[q * 6 + i] * sh.H1[q * 6 + j];
+                        sh.cand[lane] = v;
+                    } else if (lane < 27) {
+                        const int i = lane - 21;
+                        double v = 0;
+                        for (int q = 0; q < 6; ++q) v += sh.G[q * 6 + i] * sh.tot[21 + q];
+                        sh.cand[lane] = v;
+                    } else if (lane == 27) {
+                        sh.cand[27] = sh.tot[27];
+                    }
                 }
                 __syncthreads();
             };

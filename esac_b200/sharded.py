@@ -32,13 +32,8 @@ def select_global(gathered: np.ndarray, M_local: int):
     scores = gathered[:, :M_local].reshape(-1)
     sf = np.exp(scores - scores.max())
     probs = sf / sf.sum()
-    winner = 0
-    best = -1.0
-    for i, p in enumerate(probs):          # first strict maximum among p >= EPS
-        if p < 1e-8:
-            continue
-        if best < 0 or p > best:
-            best, winner = p, i
+    # first strict maximum among p >= EPS (draw(), training=false): argmax returns the first maximum
+    winner = int(np.argmax(probs)) if probs.max() >= 1e-8 else 0
     rank = winner // M_local
     assert rank < world
     pose = gathered[rank, M_local:M_local + 16].reshape(4, 4).astype(np.float32)
