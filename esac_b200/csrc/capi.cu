@@ -273,7 +273,7 @@ int run_score(esacb200_ctx* ctx, const Plan& pl) {
 int pick_group(esacb200_ctx* ctx, const Problem& P, int jobs_hint) {
     if (ctx->refine_group_opt > 0) return ctx->refine_group_opt < ctx->refine_coresident ? ctx->refine_group_opt : ctx->refine_coresident;
     const int words = (P.N + 31) / 32;
-    int g = words / 64;
+    int g = words / 100;  // ~96 CTAs at 480x640: best of the measured sweep (profiles/r01e_refine_groups.txt)
     if (g < 1) g = 1;
     int cap = ctx->refine_coresident / (jobs_hint > 0 ? jobs_hint : 1);
     if (cap < 1) cap = 1;

@@ -163,9 +163,12 @@ __device__ __forceinline__ float mufu_rcp(float x) {
     return y;
 }
 
+// tileX/Y/Z: when non-null, the tile's three coordinate rows already sit in shared memory (staged by TMA bulk copies);
+// otherwise the cells are read from global memory.
 template <int PPT, bool TAIL>
 __device__ __forceinline__ void score_item(const ScoreArgs& a, const ChunkDesc cd, const int tile, const float4* sPose,
-                                           float (*sWarp)[kMaxChunk]) {
+                                           float (*sWarp)[kMaxChunk], const float* tileX = nullptr,
+                                           const float* tileY = nullptr, const float* tileZ = nullptr) {
     constexpr int NP = PPT / 2;                 // pixel pairs per thread
     constexpr int GV = PPT >= 4 ? 4 : 2;        // pixels per load group
     constexpr int NG = PPT / GV;
@@ -180,7 +183,27 @@ __device__ __forceinline__ void score_item(const ScoreArgs& a, const ChunkDesc c
     for (int g = 0; g < NG; ++g) {
         const int p0 = tile * TP + g * (kScoreThreads * GV) + tid * GV;
         float x[GV], y[GV], z[GV];
-        if (a.vec_ok && p0 + GV <= P.N) {
+        if (tileX) {
+            const int o = g * (kScoreThreads * GV) + tid * GV;  // offset inside the tile
+            if (!TAIL) {
+                if constexpr (GV == 4) {
+                    const float4 vx = *(const float4*)(tileX + o), vy = *(const float4*)(tileY + o), vz = *(const float4*)(tileZ + o);
+                    x[0] = vx.x; x[1] = vx.y; x[GV - 2] = vx.z; x[GV - 1] = vx.w;
+                    y[0] = vy.x; y[1] = vy.y; y[GV - 2] = vy.z; y[GV - 1] = vy.w;
+                    z[0] = vz.x; z[1] = vz.y; z[GV - 2] = vz.z; z[GV - 1] = vz.w;
+                } else {
+                    const float2 vx = *(const float2*)(tileX + o), vy = *(const float2*)(tileY + o), vz = *(const float2*)(tileZ + o);
+                    x[0] = vx.x; x[1] = vx.y; y[0] = vy.x; y[1] = vy.y; z[0] = vz.x; z[1] = vz.y;
+                }
+            } else {
+                const int last = P.N - 1 - tile * TP;  // only the first (N - tile*TP) cells of a ragged tile were copied
+#pragma unroll
+                for (int i = 0; i < GV; ++i) {
+                    const int q = min(o + i, last);
+                    x[i] = tileX[q]; y[i] = tileY[q]; z[i] = tileZ[q];
+                }
+            }
+        } else if (a.vec_ok && p0 + GV <= P.N) {
             if constexpr (GV == 4) {
                 float4 vx = __ldg((const float4*)(pl + p0));
                 float4 vy = __ldg((const float4*)(pl + P.N + p0));
@@ -317,9 +340,109 @@ __global__ void __launch_bounds__(kScoreThreads, 2) score_kernel(const __grid_co
     }
 }
 
+// ---------------------------------------------------------------------------------------------
+// TMA-staged variant: the three rows of a pixel tile are brought into shared memory by cp.async.bulk (UBLKCP) copies that
+// complete on an mbarrier; while a CTA scores one (chunk, tile) item the copies for its next item are already in
+// flight in the other stage.  Needs 16-byte aligned planes and N % 4 == 0 (else score_kernel above is used).
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, int count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "WAIT_%=:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra DONE_%=;\n\t"
+        "bra WAIT_%=;\n\t"
+        "DONE_%=:\n\t}" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void tma_bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)),
+                 "l"(src), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+
+template <int PPT>
+__global__ void __launch_bounds__(kScoreThreads, 2) score_kernel_tma(const __grid_constant__ ScoreArgs a) {
+    constexpr int TP = kScoreThreads * PPT;
+    extern __shared__ __align__(128) float sTile[];  // [2 stages][3 rows][TP]
+    __shared__ float4 sPose[kMaxChunk * 3];
+    __shared__ float sWarp[kScoreThreads / 32][kMaxChunk];
+    __shared__ __align__(8) uint64_t sBar[2];
+    __shared__ int sItem[2];
+    const int tid = threadIdx.x;
+    const int n_items = *a.n_chunks * a.T;
+    const bool ragged = (a.P.N % TP) != 0;
+
+    auto issue = [&](int item, int stage) {  // thread 0: start the three row copies of `item` into `stage`
+        const int chunk = item / a.T, tile = item - chunk * a.T;
+        const int e = a.chunks[chunk].expert;
+        const int cells = min(TP, a.P.N - tile * TP);
+        const uint32_t bytes = (uint32_t)cells * 4u;
+        const float* src = a.coords + (size_t)e * 3 * a.P.N + (size_t)tile * TP;
+        float* dst = sTile + (size_t)stage * 3 * TP;
+        mbar_expect_tx(&sBar[stage], 3u * bytes);
+        tma_bulk_g2s(dst, src, bytes, &sBar[stage]);
+        tma_bulk_g2s(dst + TP, src + a.P.N, bytes, &sBar[stage]);
+        tma_bulk_g2s(dst + 2 * TP, src + 2 * (size_t)a.P.N, bytes, &sBar[stage]);
+    };
+
+    if (tid == 0) {
+        mbar_init(&sBar[0], 1);
+        mbar_init(&sBar[1], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        const int first = atomicAdd(a.work_counter, 1);
+        sItem[0] = first;
+        if (first < n_items) issue(first, 0);
+    }
+    __syncthreads();
+    uint32_t phase[2] = {0u, 0u};
+    for (int it = 0;; ++it) {
+        const int stage = it & 1;
+        const int item = sItem[stage];
+        if (item >= n_items) break;
+        if (tid == 0) {  // claim the next item and start its copies into the other stage (free since the last barrier)
+            const int nxt = atomicAdd(a.work_counter, 1);
+            sItem[stage ^ 1] = nxt;
+            if (nxt < n_items) {
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                issue(nxt, stage ^ 1);
+            }
+        }
+        const int chunk = item / a.T, tile = item - chunk * a.T;
+        const ChunkDesc cd = a.chunks[chunk];
+        const float4* src = (const float4*)(a.poses + cd.slot0);
+        for (int i = tid; i < cd.count * 3; i += kScoreThreads) sPose[i] = src[i];
+        mbar_wait(&sBar[stage], phase[stage]);
+        phase[stage] ^= 1u;
+        __syncthreads();
+        const float* tx = sTile + (size_t)stage * 3 * TP;
+        if (ragged && tile == a.T - 1) score_item<PPT, true>(a, cd, tile, sPose, sWarp, tx, tx + TP, tx + 2 * TP);
+        else score_item<PPT, false>(a, cd, tile, sPose, sWarp, tx, tx + TP, tx + 2 * TP);
+        __syncthreads();  // everyone is done with this stage, sPose, sWarp and has read sItem[stage ^ 1]'s predecessor
+    }
+}
+
 int score_tile_pixels(int ppt) { return kScoreThreads * ppt; }
 
 void launch_score(const ScoreArgs& a, int ppt, int grid, cudaStream_t st) {
+    if (a.vec_ok && ppt >= 4) {  // TMA path (bulk copies need 16-byte granularity)
+        const size_t smem = (size_t)2 * 3 * kScoreThreads * ppt * sizeof(float);
+        static bool attr_set[2] = {false, false};
+        if (ppt == 8) {
+            if (!attr_set[0]) { cudaFuncSetAttribute(score_kernel_tma<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); attr_set[0] = true; }
+            score_kernel_tma<8><<<grid, kScoreThreads, smem, st>>>(a);
+        } else {
+            if (!attr_set[1]) { cudaFuncSetAttribute(score_kernel_tma<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); attr_set[1] = true; }
+            score_kernel_tma<4><<<grid, kScoreThreads, smem, st>>>(a);
+        }
+        return;
+    }
     if (ppt == 8) score_kernel<8><<<grid, kScoreThreads, 0, st>>>(a);
     else if (ppt == 4) score_kernel<4><<<grid, kScoreThreads, 0, st>>>(a);
     else score_kernel<2><<<grid, kScoreThreads, 0, st>>>(a);

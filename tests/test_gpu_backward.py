@@ -62,3 +62,23 @@ def test_backward_cuda_tensors(api):
                       torch.from_numpy(sc.gt_pose).cuda(), 1.0, 100.0, 100.0, *sc.params)
     assert l1 == l2
     assert torch.equal(g_cpu, g_gpu.cpu())
+
+
+def test_autograd_wrapper_matches_manual_gradients(api):
+    """EsacLoss = esac.backward + the trainer's hand-made gating gradient (train_esac.py:171-180)."""
+    import torch
+    from esac_b200.autograd import esac_loss
+    sc = make_scene(E=3, H=24, W=32, M=24, sub=8, seed=12)
+    coords = torch.from_numpy(sc.coords).cuda().requires_grad_(True)
+    gating = torch.log_softmax(torch.zeros(1, 3, device="cuda"), dim=1).requires_grad_(True)
+    assign = torch.from_numpy(sc.assign)
+    api.set_seed(9)
+    loss = esac_loss(coords, gating, assign, torch.from_numpy(sc.gt_pose), 1.0, 100.0, 100.0, *sc.params)
+    loss.backward()
+    api.set_seed(9)
+    g = np.zeros_like(sc.coords)
+    l_ref = api.backward(sc.coords, g, sc.assign, sc.gt_pose, 1.0, 100.0, 100.0, *sc.params)
+    assert abs(float(loss) - l_ref) < 1e-6 * max(1.0, abs(l_ref))
+    assert np.array_equal(coords.grad.cpu().numpy(), g)
+    hist = np.bincount(sc.assign, minlength=3).astype(np.float32)
+    assert np.allclose(gating.grad.cpu().numpy().ravel(), l_ref * hist, rtol=1e-6)

@@ -1,0 +1,86 @@
+"""BASELINE.json's full size (480x640, subSampling 1, 256 hypotheses x 7 experts): size-independent properties and
+spot checks against the C oracle restatement (fast enough for a handful of hypotheses at this size)."""
+import numpy as np
+import pytest
+
+from esac_b200.synth import make_scene, pose_error
+from oracle.build import c_score
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def api():
+    import esac_b200.api as api
+    api.context().set_option("fixed_seed", 1)
+    return api
+
+
+@pytest.fixture(scope="module")
+def scene():
+    return make_scene(E=7, H=480, W=640, M=256, sub=1, seed=0, per_expert=True, active_only=False)
+
+
+def test_known_answer_at_full_resolution(api):
+    sc = make_scene(E=2, H=480, W=640, M=64, sub=1, seed=5, outlier_frac=0.3, noise=0.0)
+    out = np.zeros((4, 4), np.float32)
+    api.set_seed(1)
+    e = api.forward(sc.coords, sc.assign, out, *sc.params)
+    rot, trans = pose_error(out, sc.gt_pose)
+    assert e == sc.gt_expert and rot < 2e-3 and trans < 2e-4  # float32 coordinates limit the recovery
+
+
+def test_scores_spot_check_against_c_oracle(api, scene):
+    sc = scene
+    api.set_seed(11)
+    out = np.zeros((4, 4), np.float32)
+    api.forward(sc.coords, sc.assign, out, *sc.params)
+    hy = api.last_hypotheses()
+    idx = np.array([0, 100, 300, 511, 700, 1000, 1500, 1791])
+    ref, _ = c_score(sc.coords, sc.assign[idx], hy["poses"][idx], *sc.params)
+    assert np.abs(ref - hy["scores"][idx]).max() < 1e-4
+
+
+def test_scores_are_permutation_invariant_and_deterministic(api, scene):
+    sc = scene
+    rng = np.random.default_rng(0)
+    M = len(sc.assign)
+    poses = np.zeros((M, 6))
+    poses[:, :3] = rng.normal(0, 0.3, (M, 3))
+    poses[:, 3:] = rng.normal(0, 2.0, (M, 3))
+    s0 = api.score_poses(sc.coords, sc.assign, poses, *sc.params)
+    s1 = api.score_poses(sc.coords, sc.assign, poses, *sc.params)
+    assert np.array_equal(s0, s1)  # bit-reproducible (fixed-order reductions)
+    perm = rng.permutation(M)
+    s2 = api.score_poses(sc.coords, sc.assign[perm], poses[perm], *sc.params)
+    assert np.abs(s2 - s0[perm]).max() < 1e-9  # chunking changes, per-hypothesis arithmetic does not
+
+
+def test_score_scales_linearly_with_alpha(api, scene):
+    sc = scene
+    rng = np.random.default_rng(1)
+    M = 64
+    poses = np.zeros((M, 6))
+    poses[:, :3] = rng.normal(0, 0.2, (M, 3))
+    poses[:, 3:] = rng.normal(0, 1.0, (M, 3)) + [0, 0, 2]
+    a = list(sc.params)
+    s1 = api.score_poses(sc.coords, sc.assign[:M], poses, *a)
+    a[6] = 200.0  # inlierAlpha
+    s2 = api.score_poses(sc.coords, sc.assign[:M], poses, *a)
+    assert np.abs(s2 - 2 * s1).max() < 1e-5
+    assert s1.min() >= 0 and s1.max() <= 100.0
+
+
+def test_forward_is_reproducible_and_winner_is_local_argmax(api, scene):
+    sc = scene
+    outs = []
+    for _ in range(2):
+        api.set_seed(21)
+        out = np.zeros((4, 4), np.float32)
+        e = api.forward(sc.coords, sc.assign, out, *sc.params)
+        outs.append((e, out.copy(), api.last_hypotheses()["scores"], api.last_stats()["winner"]))
+    assert outs[0][0] == outs[1][0] and np.array_equal(outs[0][1], outs[1][1]) and np.array_equal(outs[0][2], outs[1][2])
+    assert outs[0][3] == int(np.argmax(outs[0][2]))
+    assert outs[0][0] == sc.gt_expert
+    rot, trans = pose_error(outs[0][1], sc.gt_pose)
+    assert rot < 0.1 and trans < 0.01
