@@ -66,7 +66,7 @@ struct esacb200_ctx {
     // workspace
     DevBuf coords, grads, assign64, assign32, counts, offsets, perm, slot_of, chunks, scalars, centres, poses, poses_ref,
         cells, tries, posepk, part, scores, probs, stats, contrib, masks, rounds, scratch, barrier, out17, inject,
-        losses, red, hypgrad, job_of, gt, smp_int, smp_surv;
+        losses, red, hypgrad, job_of, gt, smp_int, smp_surv, coords4;
     float* h_out = nullptr;  // pinned staging: 32 floats
     double* h_dbl = nullptr; // pinned staging: 8 doubles
     int inj_M = 0, inj_T = 0;
@@ -229,7 +229,8 @@ int run_sample(esacb200_ctx* ctx, const Plan& pl, uint64_t seed) {
     st.surv = ctx->smp_surv.as<int2>();
     st.cap = cap;
     st.M = P.M;
-    ctx->st.kernel_launches += launch_sample(pl.d_coords, ctx->assign32.as<int>(), P, seed, ctx->max_tries,
+    CK(ctx->coords4.ensure((size_t)P.E * P.N * sizeof(float4)));
+    ctx->st.kernel_launches += launch_sample(pl.d_coords, ctx->coords4.as<float4>(), ctx->assign32.as<int>(), P, seed, ctx->max_tries,
                                              ctx->inj_M ? ctx->inject.as<int>() : nullptr, ctx->inj_T, st, ctx->sm_count, ctx->sample_prefilter,
                                              ctx->poses.as<Pose>(), ctx->cells.as<int>(), ctx->tries.as<int>(), ctx->stream);
     CK(cudaGetLastError());
@@ -385,7 +386,7 @@ void esacb200_destroy(esacb200_ctx* ctx) {
                       &ctx->slot_of, &ctx->chunks, &ctx->scalars, &ctx->centres, &ctx->poses, &ctx->poses_ref, &ctx->cells,
                       &ctx->tries, &ctx->posepk, &ctx->part, &ctx->scores, &ctx->probs, &ctx->stats, &ctx->contrib,
                       &ctx->masks, &ctx->rounds, &ctx->scratch, &ctx->barrier, &ctx->out17, &ctx->inject, &ctx->losses,
-                      &ctx->red, &ctx->hypgrad, &ctx->job_of, &ctx->gt, &ctx->smp_int, &ctx->smp_surv};
+                      &ctx->red, &ctx->hypgrad, &ctx->job_of, &ctx->gt, &ctx->smp_int, &ctx->smp_surv, &ctx->coords4};
     for (DevBuf* b : bufs) b->release();
     for (int i = 0; i < EV_COUNT; ++i)
         if (ctx->ev[i]) cudaEventDestroy(ctx->ev[i]);

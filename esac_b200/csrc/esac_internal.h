@@ -105,7 +105,7 @@ struct SampleState {
     int M;
 };
 // Returns the number of kernel launches it enqueued.
-int launch_sample(const float* coords, const int* assign32, const Problem& P, uint64_t seed, int max_tries,
+int launch_sample(const float* coords, float4* coords4, const int* assign32, const Problem& P, uint64_t seed, int max_tries,
                   const int* injected, int inj_T, const SampleState& st, int sm_count, int use_prefilter, Pose* poses, int* cells,
                   int* tries, cudaStream_t st_);
 

@@ -32,7 +32,7 @@ constexpr unsigned long long kNoKey = ~0ull;   // best[h]: (try << 32) | staging
 constexpr unsigned kNoSlot = 0xffffffffu;
 
 struct SampleArgs {
-    const float* coords;
+    const float4* coords4;  // [E][N] interleaved (x, y, z, -) copy of the coordinate planes: one 16-byte sector per gathered cell
     const int* assign32;
     Problem P;
     uint64_t seed;
@@ -51,10 +51,11 @@ __device__ __forceinline__ void load_try(const SampleArgs& a, int h, int t, int 
     } else {
         draw_minimal_set(a.seed, (uint32_t)h, (uint32_t)t, P.W, P.H, cx, cy);
     }
-    const float* pl = a.coords + (size_t)a.assign32[h] * 3 * P.N;
+    const float4* pl = a.coords4 + (size_t)a.assign32[h] * P.N;
     for (int j = 0; j < 4; ++j) {
         const int p = cy[j] * P.W + cx[j];
-        obj[j][0] = pl[p]; obj[j][1] = pl[P.N + p]; obj[j][2] = pl[2 * (size_t)P.N + p];
+        const float4 v = __ldg(pl + p);
+        obj[j][0] = v.x; obj[j][1] = v.y; obj[j][2] = v.z;
         img[j][0] = (float)(cx[j] * P.sub + P.sub / 2 - P.shiftX);
         img[j][1] = (float)(cy[j] * P.sub + P.sub / 2 - P.shiftY);
     }
@@ -66,6 +67,17 @@ __device__ __noinline__ bool exact_try(const SampleArgs& a, int h, int t, Pose& 
     const double f = (double)a.P.f, ppx = (double)a.P.ppx, ppy = (double)a.P.ppy;
     solved = p3p_pose(obj, img, f, ppx, ppy, pose);
     return solved && minimal_set_gate(obj, img, pose, f, ppx, ppy, a.P.tau);
+}
+
+// [E,3,N] planes -> [E,N] float4 cells.  The sampling stage gathers 4 random cells per try, millions of times per
+// call; with planar storage every cell costs three 32-byte sectors of L2 traffic, interleaved it costs one.
+__global__ void interleave_kernel(const float* __restrict__ coords, float4* __restrict__ out, int E, int N) {
+    const size_t total = (size_t)E * N;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+        const size_t e = i / N, p = i - e * N;
+        const float* pl = coords + e * 3 * (size_t)N;
+        out[i] = make_float4(pl[p], pl[N + p], pl[2 * (size_t)N + p], 0.f);
+    }
 }
 
 // state init: every hypothesis unresolved, window at try 0
@@ -230,14 +242,15 @@ __global__ void __launch_bounds__(64) emit_kernel(const __grid_constant__ Sample
     tries[h] = t + 1;
 }
 
-int launch_sample(const float* coords, const int* assign32, const Problem& P, uint64_t seed, int max_tries,
+int launch_sample(const float* coords, float4* coords4, const int* assign32, const Problem& P, uint64_t seed, int max_tries,
                   const int* injected, int inj_T, const SampleState& st, int sm_count, int use_prefilter, Pose* poses, int* cells,
                   int* tries, cudaStream_t stream) {
     SampleArgs a;
-    a.coords = coords; a.assign32 = assign32; a.P = P; a.seed = seed;
+    a.coords4 = coords4; a.assign32 = assign32; a.P = P; a.seed = seed;
     a.limit = injected ? (max_tries < inj_T ? max_tries : inj_T) : max_tries;
     a.injected = injected; a.inj_T = inj_T; a.st = st; a.use_prefilter = use_prefilter;
     int launches = 0;
+    interleave_kernel<<<sm_count * 8, 256, 0, stream>>>(coords, coords4, P.E, P.N); ++launches;
     sample_init_kernel<<<(P.M + 255) / 256, 256, 0, stream>>>(st, P.M); ++launches;
     const int kWaves = 7;
     const int grid = sm_count * 16;

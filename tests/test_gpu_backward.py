@@ -78,7 +78,7 @@ def test_autograd_wrapper_matches_manual_gradients(api):
     api.set_seed(9)
     g = np.zeros_like(sc.coords)
     l_ref = api.backward(sc.coords, g, sc.assign, sc.gt_pose, 1.0, 100.0, 100.0, *sc.params)
-    assert abs(float(loss) - l_ref) < 1e-6 * max(1.0, abs(l_ref))
+    assert abs(loss.item() - l_ref) < 1e-6 * max(1.0, abs(l_ref))
     assert np.array_equal(coords.grad.cpu().numpy(), g)
     hist = np.bincount(sc.assign, minlength=3).astype(np.float32)
     assert np.allclose(gating.grad.cpu().numpy().ravel(), l_ref * hist, rtol=1e-6)
