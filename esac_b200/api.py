@@ -59,6 +59,8 @@ def load_library() -> C.CDLL:
     cam = [i32, i32, f32, f32, f32, f32, f32, f32, f32, i32]  # shiftX .. subSampling
     lib.esacb200_forward.argtypes = [vp, vp, i32, i32, i32, vp, i64, i32, vp] + cam + [C.POINTER(i32)]
     lib.esacb200_backward.argtypes = [vp, vp, vp, i32, i32, i32, vp, i64, i32, vp, f32, f32, f32] + cam + [C.POINTER(f64)]
+    lib.esacb200_forward_batch.argtypes = [vp, i32, vp, i32, i32, i32, vp, i64, i32, vp] + cam + [vp]
+    lib.esacb200_forward_batch.restype = i32
     lib.esacb200_score_poses.argtypes = [vp, vp, i32, i32, i32, vp, i64, i32, vp] + cam + [vp]
     lib.esacb200_refine_poses.argtypes = [vp, vp, i32, i32, i32, vp, i64, i32, vp, i32, i32, f32, f32, f32, f32, f32, i32, vp, vp]
     lib.esacb200_get_stats.argtypes = [vp, C.POINTER(Stats)]
@@ -343,6 +345,32 @@ def backward(sceneCoordinates, outGradients, hypAssignment, gtPose, wLossRot, wL
 # ------------------------------------------------------------------------------------------------
 # additive entry points
 # ------------------------------------------------------------------------------------------------
+def forward_batch(sceneCoordinates, hypAssignment, outPoses, shiftX, shiftY, focalLength, ppointX, ppointY,
+                  inlierThreshold, inlierAlpha, inlierBeta, maxReproj, subSampling) -> list:
+    """esac.forward over a batch: sceneCoordinates [B,E,3,H,W] float32, hypAssignment [B,M] int64 (contiguous rows),
+    outPoses [B,4,4] float32 written in place.  Returns the winning expert of every image.  One host synchronisation
+    for the whole batch; host tensors (pinned) are copied on a second stream while the previous image computes."""
+    _check(sceneCoordinates, "Float", 5, "sceneCoordinates")
+    _check(hypAssignment, "Long", 2, "hypAssignment")
+    _check(outPoses, "Float", 3, "outPoses")
+    B, E, C3, H, W = (int(v) for v in sceneCoordinates.shape)
+    if C3 != 3 or tuple(outPoses.shape) != (B, 4, 4) or int(hypAssignment.shape[0]) != B:
+        raise RuntimeError("shapes must be [B,E,3,H,W], [B,M], [B,4,4]")
+    co = _Arg(sceneCoordinates)
+    op = _Arg(outPoses, writable=True)
+    ha = _Arg(hypAssignment)
+    M = int(hypAssignment.shape[1])
+    ctx = _pick_ctx(co.device, op.device, ha.device)
+    experts = (C.c_int * B)()
+    ctx.check(ctx.lib.esacb200_forward_batch(ctx.handle, B, co.ptr, E, H, W, ha.ptr, 1, M, op.ptr, int(shiftX), int(shiftY),
+                                             float(focalLength), float(ppointX), float(ppointY), float(inlierThreshold),
+                                             float(inlierAlpha), float(inlierBeta), float(maxReproj), int(subSampling),
+                                             experts))
+    op.finish()
+    return [int(e) for e in experts]
+
+
+
 def score_poses(sceneCoordinates, hypAssignment, poses6, shiftX, shiftY, focalLength, ppointX, ppointY,
                 inlierThreshold, inlierAlpha, inlierBeta, maxReproj, subSampling) -> np.ndarray:
     """Soft-inlier scores (getReproErrs + getHypScores) of given scene poses [M, 6] = (rvec, tvec)."""

@@ -52,6 +52,8 @@ struct esacb200_ctx {
     int sm_count = 0;
     char dev_name[128] = {0};
     cudaStream_t own_stream = nullptr;
+    cudaStream_t copy_stream = nullptr;
+    cudaEvent_t ev_copied[2] = {nullptr, nullptr}, ev_consumed[2] = {nullptr, nullptr};
     cudaStream_t stream = nullptr;
     uint64_t seed = 1305;  // thread_rand.h:103
     uint64_t calls = 0;
@@ -66,7 +68,7 @@ struct esacb200_ctx {
     // workspace
     DevBuf coords, grads, assign64, assign32, counts, offsets, perm, slot_of, chunks, scalars, centres, poses, poses_ref,
         cells, tries, posepk, part, scores, probs, stats, contrib, masks, rounds, scratch, barrier, out17, inject,
-        losses, red, hypgrad, job_of, gt, smp_int, smp_surv, coords4;
+        losses, red, hypgrad, job_of, gt, smp_int, smp_surv, coords4, coords_alt, assign64_alt, out_batch;
     float* h_out = nullptr;  // pinned staging: 32 floats
     double* h_dbl = nullptr; // pinned staging: 8 doubles
     int inj_M = 0, inj_T = 0;
@@ -141,16 +143,17 @@ int fill_problem(esacb200_ctx* ctx, Problem& P, int E, int H, int W, int M, int 
     return 0;
 }
 
-// Upload (or alias) the inputs and run the prep kernel.
-int stage_inputs(esacb200_ctx* ctx, Plan& pl, const float* coords, const int64_t* assign, int64_t stride) {
+// Upload (or alias) the inputs.  Host coordinate maps go to `cbuf` on `copy_stream` (pinned memory: asynchronous).
+int upload_inputs(esacb200_ctx* ctx, Plan& pl, const float* coords, const int64_t* assign, int64_t stride, DevBuf& cbuf,
+                  DevBuf& abuf, cudaStream_t copy_stream) {
     const Problem& P = pl.P;
     const size_t cbytes = (size_t)P.E * 3 * P.N * sizeof(float);
     if (is_device_ptr(coords)) {
         pl.d_coords = coords;
     } else {
-        CK(ctx->coords.ensure(cbytes));
-        CK(cudaMemcpyAsync(ctx->coords.p, coords, cbytes, cudaMemcpyHostToDevice, ctx->stream));
-        pl.d_coords = ctx->coords.as<float>();
+        CK(cbuf.ensure(cbytes));
+        CK(cudaMemcpyAsync(cbuf.p, coords, cbytes, cudaMemcpyHostToDevice, copy_stream));
+        pl.d_coords = cbuf.as<float>();
     }
     if (is_device_ptr(assign)) {
         pl.d_assign = (const long long*)assign;
@@ -158,13 +161,18 @@ int stage_inputs(esacb200_ctx* ctx, Plan& pl, const float* coords, const int64_t
     } else {
         std::vector<long long> tmp((size_t)P.M);
         for (int h = 0; h < P.M; ++h) tmp[h] = (long long)assign[(long long)h * stride];
-        CK(ctx->assign64.ensure((size_t)P.M * 8));
+        CK(abuf.ensure((size_t)P.M * 8));
         // pageable source: the copy is staged before cudaMemcpyAsync returns, so tmp may die
-        CK(cudaMemcpyAsync(ctx->assign64.p, tmp.data(), (size_t)P.M * 8, cudaMemcpyHostToDevice, ctx->stream));
-        pl.d_assign = ctx->assign64.as<long long>();
+        CK(cudaMemcpyAsync(abuf.p, tmp.data(), (size_t)P.M * 8, cudaMemcpyHostToDevice, copy_stream));
+        pl.d_assign = abuf.as<long long>();
         pl.assign_stride = 1;
     }
-    mark(ctx, EV_H2D);
+    return 0;
+}
+
+// Scoring launch shape, workspace, prep kernel.
+int plan_and_prep(esacb200_ctx* ctx, Plan& pl) {
+    const Problem& P = pl.P;
     // scoring launch shape
     int ppt = 8, hc = 64;
     const int want = 2 * 2 * ctx->sm_count;
@@ -212,6 +220,13 @@ int stage_inputs(esacb200_ctx* ctx, Plan& pl, const float* coords, const int64_t
     ctx->st.kernel_launches += 1;
     mark(ctx, EV_PREP);
     return 0;
+}
+
+int stage_inputs(esacb200_ctx* ctx, Plan& pl, const float* coords, const int64_t* assign, int64_t stride) {
+    int rc = upload_inputs(ctx, pl, coords, assign, stride, ctx->coords, ctx->assign64, ctx->stream);
+    if (rc) return rc;
+    mark(ctx, EV_H2D);
+    return plan_and_prep(ctx, pl);
 }
 
 int run_sample(esacb200_ctx* ctx, const Plan& pl, uint64_t seed) {
@@ -319,6 +334,31 @@ int run_refine(esacb200_ctx* ctx, const Plan& pl, const Pose* in, Pose* out, con
     return 0;
 }
 
+uint64_t call_seed(esacb200_ctx* ctx) {
+    uint64_t s = ctx->fixed_seed ? ctx->seed : mix64(ctx->seed + kGold * ctx->calls);
+    if (ctx->calls == 0) s = ctx->seed;
+    ++ctx->calls;
+    return s;
+}
+
+// sample -> score -> select -> refine(winner) -> camera pose + expert id into d_out17 (17 floats + flags at [17]); no sync.
+int enqueue_forward_core(esacb200_ctx* ctx, const Plan& pl, float* d_out17) {
+    const Problem& P = pl.P;
+    int* sc = ctx->scalars.as<int>();
+    const uint64_t seed = call_seed(ctx);
+    int rc = run_sample(ctx, pl, seed);
+    if (rc) return rc;
+    rc = run_score(ctx, pl);
+    if (rc) return rc;
+    const int group = pick_group(ctx, P, 1);
+    rc = run_refine(ctx, pl, ctx->poses.as<Pose>(), ctx->poses_ref.as<Pose>(), sc + S_WINNER, nullptr, 1, 1, group);
+    if (rc) return rc;
+    mark(ctx, EV_REFINE);
+    launch_finish_forward(ctx->poses_ref.as<Pose>(), sc + S_WINNER, ctx->assign32.as<int>(), sc + S_FLAGS, d_out17, ctx->stream);
+    ctx->st.kernel_launches += 1;
+    return 0;
+}
+
 void begin_call(esacb200_ctx* ctx) {
     memset(&ctx->st, 0, sizeof(ctx->st));
     for (int i = 0; i < EV_COUNT; ++i) ctx->ev_used[i] = false;
@@ -339,12 +379,6 @@ void finish_stats(esacb200_ctx* ctx) {
     s.ms_total = span(ctx, EV_START, EV_END);
 }
 
-uint64_t call_seed(esacb200_ctx* ctx) {
-    uint64_t s = ctx->fixed_seed ? ctx->seed : mix64(ctx->seed + kGold * ctx->calls);
-    if (ctx->calls == 0) s = ctx->seed;
-    ++ctx->calls;
-    return s;
-}
 
 }  // namespace
 
@@ -368,6 +402,11 @@ int esacb200_create(int device, esacb200_ctx** out) {
     snprintf(ctx->dev_name, sizeof(ctx->dev_name), "%s", prop.name);
     if (cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking) != cudaSuccess) { delete ctx; return ESACB200_ERR_CUDA; }
     ctx->stream = ctx->own_stream;
+    cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking);
+    for (int i = 0; i < 2; ++i) {
+        cudaEventCreateWithFlags(&ctx->ev_copied[i], cudaEventDisableTiming);
+        cudaEventCreateWithFlags(&ctx->ev_consumed[i], cudaEventDisableTiming);
+    }
     for (int i = 0; i < EV_COUNT; ++i) cudaEventCreate(&ctx->ev[i]);
     cudaMallocHost((void**)&ctx->h_out, 32 * sizeof(float));
     cudaMallocHost((void**)&ctx->h_dbl, 8 * sizeof(double));
@@ -386,12 +425,17 @@ void esacb200_destroy(esacb200_ctx* ctx) {
                       &ctx->slot_of, &ctx->chunks, &ctx->scalars, &ctx->centres, &ctx->poses, &ctx->poses_ref, &ctx->cells,
                       &ctx->tries, &ctx->posepk, &ctx->part, &ctx->scores, &ctx->probs, &ctx->stats, &ctx->contrib,
                       &ctx->masks, &ctx->rounds, &ctx->scratch, &ctx->barrier, &ctx->out17, &ctx->inject, &ctx->losses,
-                      &ctx->red, &ctx->hypgrad, &ctx->job_of, &ctx->gt, &ctx->smp_int, &ctx->smp_surv, &ctx->coords4};
+                      &ctx->red, &ctx->hypgrad, &ctx->job_of, &ctx->gt, &ctx->smp_int, &ctx->smp_surv, &ctx->coords4, &ctx->coords_alt, &ctx->assign64_alt, &ctx->out_batch};
     for (DevBuf* b : bufs) b->release();
     for (int i = 0; i < EV_COUNT; ++i)
         if (ctx->ev[i]) cudaEventDestroy(ctx->ev[i]);
     if (ctx->h_out) cudaFreeHost(ctx->h_out);
     if (ctx->h_dbl) cudaFreeHost(ctx->h_dbl);
+    for (int i = 0; i < 2; ++i) {
+        if (ctx->ev_copied[i]) cudaEventDestroy(ctx->ev_copied[i]);
+        if (ctx->ev_consumed[i]) cudaEventDestroy(ctx->ev_consumed[i]);
+    }
+    if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
     if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
     delete ctx;
 }
@@ -460,17 +504,8 @@ int esacb200_forward(esacb200_ctx* ctx, const float* coords, int E, int H, int W
     if (rc) return rc;
     const Problem& P = pl.P;
     int* sc = ctx->scalars.as<int>();
-    const uint64_t seed = call_seed(ctx);
-    rc = run_sample(ctx, pl, seed);
+    rc = enqueue_forward_core(ctx, pl, ctx->out17.as<float>());
     if (rc) return rc;
-    rc = run_score(ctx, pl);
-    if (rc) return rc;
-    const int group = pick_group(ctx, P, 1);
-    rc = run_refine(ctx, pl, ctx->poses.as<Pose>(), ctx->poses_ref.as<Pose>(), sc + S_WINNER, nullptr, 1, 1, group);
-    if (rc) return rc;
-    mark(ctx, EV_REFINE);
-    launch_finish_forward(ctx->poses_ref.as<Pose>(), sc + S_WINNER, ctx->assign32.as<int>(), ctx->out17.as<float>(), ctx->stream);
-    ctx->st.kernel_launches += 1;
     CK(cudaMemcpyAsync(ctx->h_out, ctx->out17.p, 17 * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
     CK(cudaMemcpyAsync(ctx->h_out + 20, sc, 8 * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
     CK(cudaMemcpyAsync(ctx->h_dbl, ctx->stats.p, 3 * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
@@ -492,6 +527,71 @@ int esacb200_forward(esacb200_ctx* ctx, const float* coords, int E, int H, int W
     ctx->last_backward = false;
     finish_stats(ctx);
     ctx->inj_M = ctx->inj_T = 0;
+    return ESACB200_OK;
+}
+
+// -------------------------------------------------------------------------------------------------
+// esac_forward over a batch of B images of one shape (BASELINE configs[2]: "batch 8 images").  The reference has no such
+// entry: its callers loop over a DataLoader with batch_size=1 (test_esac.py:137).  Images are processed back to back on
+// the compute stream with ONE host synchronisation at the end; host coordinate maps are double-buffered and copied on a
+// second stream so the copy of image b+1 overlaps the kernels of image b.
+int esacb200_forward_batch(esacb200_ctx* ctx, int B, const float* coords, int E, int H, int W, const int64_t* assign,
+                           int64_t assign_stride, int M, float* out_poses, int shiftX, int shiftY, float f, float ppx,
+                           float ppy, float tau, float alpha, float beta, float maxReproj, int sub, int* out_experts) {
+    if (!ctx) return ESACB200_ERR_ARG;
+    if (!coords || !assign || !out_poses || B <= 0) return fail(ctx, ESACB200_ERR_ARG, "null pointer argument or empty batch");
+    Plan pl;
+    int rc = fill_problem(ctx, pl.P, E, H, W, M, shiftX, shiftY, f, ppx, ppy, tau, alpha, beta, maxReproj, sub);
+    if (rc) return rc;
+    if ((long long)(W - 1) * (H - 1) < 4) return fail(ctx, ESACB200_ERR_ARG, "map %dx%d too small", W, H);
+    begin_call(ctx);
+    ctx->inj_M = ctx->inj_T = 0;
+    const size_t cstride = (size_t)E * 3 * H * W;
+    const bool host_coords = !is_device_ptr(coords);
+    const bool host_assign = !is_device_ptr(assign);
+    // element stride between the assignments of consecutive images: rows of a [B, M] tensor
+    const int64_t arow = assign_stride == 0 ? 0 : (int64_t)M * assign_stride;
+    CK(ctx->out_batch.ensure((size_t)B * 20 * sizeof(float)));
+    DevBuf* cb[2] = {&ctx->coords, &ctx->coords_alt};
+    DevBuf* ab[2] = {&ctx->assign64, &ctx->assign64_alt};
+    for (int b = 0; b < B; ++b) {
+        const int buf = b & 1;
+        if (host_coords && b >= 2) CK(cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_consumed[buf], 0));
+        rc = upload_inputs(ctx, pl, coords + (size_t)b * cstride, assign + (size_t)b * arow, assign_stride, *cb[buf], *ab[buf],
+                           host_coords ? ctx->copy_stream : ctx->stream);
+        if (rc) return rc;
+        if (host_coords) {
+            CK(cudaEventRecord(ctx->ev_copied[buf], ctx->copy_stream));
+            CK(cudaStreamWaitEvent(ctx->stream, ctx->ev_copied[buf], 0));
+        }
+        (void)host_assign;
+        if (b == 0) mark(ctx, EV_H2D);
+        rc = plan_and_prep(ctx, pl);
+        if (rc) return rc;
+        rc = enqueue_forward_core(ctx, pl, ctx->out_batch.as<float>() + (size_t)b * 20);
+        if (rc) return rc;
+        if (host_coords) CK(cudaEventRecord(ctx->ev_consumed[buf], ctx->stream));
+    }
+    std::vector<float> host((size_t)B * 20);
+    CK(cudaMemcpyAsync(host.data(), ctx->out_batch.p, host.size() * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
+    const bool dev_out = is_device_ptr(out_poses);
+    if (dev_out)
+        CK(cudaMemcpy2DAsync(out_poses, 16 * sizeof(float), ctx->out_batch.p, 20 * sizeof(float), 16 * sizeof(float), B,
+                             cudaMemcpyDeviceToDevice, ctx->stream));
+    mark(ctx, EV_END);
+    CK(cudaStreamSynchronize(ctx->stream));
+    CK(cudaGetLastError());
+    for (int b = 0; b < B; ++b) {
+        const float* o = host.data() + (size_t)b * 20;
+        if (o[17] != 0.f) return fail(ctx, ESACB200_ERR_ARG, "image %d: hypAssignment holds an expert index outside [0, %d)", b, E);
+        if (!dev_out) memcpy(out_poses + (size_t)b * 16, o, 16 * sizeof(float));
+        if (out_experts) out_experts[b] = (int)o[16];
+    }
+    ctx->st.M = M;
+    ctx->st.winner = (int)host[(size_t)(B - 1) * 20 + 18];
+    ctx->last_M = M;
+    ctx->last_backward = false;
+    finish_stats(ctx);
     return ESACB200_OK;
 }
 
@@ -611,7 +711,9 @@ int esacb200_backward(esacb200_ctx* ctx, const float* coords, float* grads, int 
     if (rc) return rc;
     // refHyps = initHyps for everything below PROB_THRESH (esac.cpp:331-334)
     CK(cudaMemcpyAsync(ctx->poses_ref.p, ctx->poses.p, (size_t)M * sizeof(Pose), cudaMemcpyDeviceToDevice, ctx->stream));
-    int group = pick_group(ctx, P, 8);
+    // ~64 concurrent jobs: the refinement of many hypotheses is fp64-throughput bound, small groups keep every SM busy
+    // without paying the inter-CTA barrier (profiles/r01f_backward_timing.txt)
+    int group = pick_group(ctx, P, 64);
     rc = run_refine(ctx, pl, ctx->poses.as<Pose>(), ctx->poses_ref.as<Pose>(), ctx->contrib.as<int>(), sc + S_NCONTRIB, 0, M, group);
     if (rc) return rc;
     mark(ctx, EV_REFINE);

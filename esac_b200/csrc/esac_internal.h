@@ -132,8 +132,10 @@ struct RefineArgs {
 };
 void launch_refine(const RefineArgs& a, int n_groups, cudaStream_t st);
 int refine_max_coresident_blocks(int sm_count);
-// camera->world 4x4 float of poses[*idx] + expert id, packed for one D2H copy: out[0..15], out[16]=expert
-void launch_finish_forward(const Pose* poses, const int* winner, const int* assign32, float* out17, cudaStream_t st);
+// camera->world 4x4 float of poses[*winner] packed for one D2H copy: out[0..15], out[16] = expert id,
+// out[17] = bad-assignment flag, out[18] = winning hypothesis
+void launch_finish_forward(const Pose* poses, const int* winner, const int* assign32, const int* flags, float* out20,
+                           cudaStream_t st);
 
 // --- bwd.cu -------------------------------------------------------------------------------
 struct BwdArgs {

@@ -330,7 +330,9 @@ __global__ void __launch_bounds__(kRefThreads, 1) refine_kernel(const __grid_con
                         else sh.flag = 0;
                     }
                     __syncthreads();
-                    if (sh.flag == 0) break;
+                    const int retry = sh.flag;
+                    __syncthreads();  // every thread has read the flag before thread 0 may rewrite it below
+                    if (retry == 0) break;
                 }
                 if (tid == 0) {
                     sh.lamlg = sh.lamlg - 1 > -16 ? sh.lamlg - 1 : -16;
@@ -344,7 +346,9 @@ __global__ void __launch_bounds__(kRefThreads, 1) refine_kernel(const __grid_con
                     }
                 }
                 __syncthreads();
-                if (sh.flag) break;
+                const int done = sh.flag;
+                __syncthreads();
+                if (done) break;
             }
             Pose np_;
             for (int i = 0; i < 3; ++i) { np_.r[i] = sh.par[i]; np_.t[i] = sh.par[3 + i]; }
@@ -383,18 +387,21 @@ int refine_max_coresident_blocks(int sm_count) {
     return nb * sm_count;
 }
 
-__global__ void finish_forward_kernel(const Pose* poses, const int* winner, const int* assign32, float* out17) {
+__global__ void finish_forward_kernel(const Pose* poses, const int* winner, const int* assign32, const int* flags, float* out) {
     if (threadIdx.x == 0) {
         const int w = *winner;
         double T[16];
         pose2trans(poses[w], T);
-        for (int i = 0; i < 16; ++i) out17[i] = (float)T[i];
-        out17[16] = (float)assign32[w];
+        for (int i = 0; i < 16; ++i) out[i] = (float)T[i];
+        out[16] = (float)assign32[w];
+        out[17] = (float)flags[0];
+        out[18] = (float)w;
     }
 }
 
-void launch_finish_forward(const Pose* poses, const int* winner, const int* assign32, float* out17, cudaStream_t st) {
-    finish_forward_kernel<<<1, 32, 0, st>>>(poses, winner, assign32, out17);
+void launch_finish_forward(const Pose* poses, const int* winner, const int* assign32, const int* flags, float* out20,
+                           cudaStream_t st) {
+    finish_forward_kernel<<<1, 32, 0, st>>>(poses, winner, assign32, flags, out20);
 }
 
 }  // namespace esacb200

@@ -74,6 +74,15 @@ int esacb200_backward(esacb200_ctx* ctx, const float* coords, float* grads, int 
                       int subSampling, double* out_loss);
 
 /* ---- additive entry points ------------------------------------------------------------------ */
+/* esac_forward over B images of one shape (the reference's callers loop with batch_size=1, test_esac.py:137):
+ * coords float32 [B,E,3,H,W], assign int64 [B,M] (rows contiguous, element stride assign_stride; 0 = one expert for all),
+ * out_poses float32 [B,4,4], out_experts int [B] (host).  One host synchronisation for the whole batch; host maps are
+ * double-buffered and copied on a second stream, overlapping the previous image's kernels. */
+int esacb200_forward_batch(esacb200_ctx* ctx, int B, const float* coords, int E, int H, int W, const int64_t* assign,
+                           int64_t assign_stride, int M, float* out_poses, int shiftX, int shiftY, float focalLength,
+                           float ppointX, float ppointY, float inlierThreshold, float inlierAlpha, float inlierBeta,
+                           float maxReproj, int subSampling, int* out_experts);
+
 /* Soft-inlier scores of given poses (getReproErrs + getHypScores, esac_util.h:235-363) without
  * sampling/selection/refinement: poses6 = host double [M][6] (rvec, tvec); out_scores host double [M]. */
 int esacb200_score_poses(esacb200_ctx* ctx, const float* coords, int E, int H, int W, const int64_t* assign,

@@ -187,3 +187,35 @@ def test_sampling_prefilter_does_not_change_results(api, kw):
     assert np.array_equal(res[0]["tries"], res[1]["tries"])
     assert np.array_equal(res[0]["cells"], res[1]["cells"])
     assert np.array_equal(res[0]["poses"], res[1]["poses"])
+
+
+def test_forward_batch_equals_a_loop_of_forward(api):
+    """BASELINE configs[2] shape of work (a batch of images): the batched entry must give what a loop of esac.forward
+    gives (the call counter advances the sampling stream identically), for host and for CUDA tensors."""
+    import torch
+    B = 4
+    scenes = [make_scene(E=3, H=30, W=40, M=48, sub=8, seed=60 + b) for b in range(B)]
+    coords = np.stack([s.coords for s in scenes]); assign = np.stack([s.assign for s in scenes])
+    api.set_option("fixed_seed", 0)
+    try:
+        api.set_seed(123)
+        ref_e, ref_p = [], []
+        for s in scenes:
+            out = np.zeros((4, 4), np.float32)
+            ref_e.append(api.forward(s.coords, s.assign, out, *scenes[0].params))
+            ref_p.append(out)
+        api.set_seed(123)
+        outs = np.zeros((B, 4, 4), np.float32)
+        e = api.forward_batch(coords, assign, outs, *scenes[0].params)
+        assert e == ref_e and np.array_equal(outs, np.stack(ref_p))
+        api.set_seed(123)
+        outs_gpu = torch.zeros(B, 4, 4, device="cuda")
+        e2 = api.forward_batch(torch.from_numpy(coords).cuda(), torch.from_numpy(assign).cuda(), outs_gpu, *scenes[0].params)
+        assert e2 == ref_e and np.array_equal(outs_gpu.cpu().numpy(), np.stack(ref_p))
+        api.set_seed(123)
+        outs_pin = torch.zeros(B, 4, 4).pin_memory()
+        e3 = api.forward_batch(torch.from_numpy(coords).pin_memory(), torch.from_numpy(assign), outs_pin, *scenes[0].params)
+        assert e3 == ref_e and np.array_equal(outs_pin.numpy(), np.stack(ref_p))
+    finally:
+        api.set_option("fixed_seed", 1)
+    assert [s.gt_expert for s in scenes] == ref_e
