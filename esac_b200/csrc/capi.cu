@@ -711,9 +711,14 @@ int esacb200_backward(esacb200_ctx* ctx, const float* coords, float* grads, int 
     if (rc) return rc;
     // refHyps = initHyps for everything below PROB_THRESH (esac.cpp:331-334)
     CK(cudaMemcpyAsync(ctx->poses_ref.p, ctx->poses.p, (size_t)M * sizeof(Pose), cudaMemcpyDeviceToDevice, ctx->stream));
-    // ~64 concurrent jobs: the refinement of many hypotheses is fp64-throughput bound, small groups keep every SM busy
-    // without paying the inter-CTA barrier (profiles/r01f_backward_timing.txt)
-    int group = pick_group(ctx, P, 64);
+    // Refining many hypotheses is fp64-throughput bound, so every SM should be busy and no CTA should wait at an inter-CTA
+    // barrier longer than needed: one 4-byte read-back of the number of contributing hypotheses (a ~20 us stall on a
+    // multi-millisecond call) lets the group size be coresident / jobs.
+    CK(cudaMemcpyAsync(ctx->h_out + 28, sc + S_NCONTRIB, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    int n_jobs_now = *(const int*)(ctx->h_out + 28);
+    if (n_jobs_now < 1) n_jobs_now = 1;
+    int group = pick_group(ctx, P, n_jobs_now);
     rc = run_refine(ctx, pl, ctx->poses.as<Pose>(), ctx->poses_ref.as<Pose>(), ctx->contrib.as<int>(), sc + S_NCONTRIB, 0, M, group);
     if (rc) return rc;
     mark(ctx, EV_REFINE);
