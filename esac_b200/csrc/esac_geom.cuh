@@ -719,61 +719,6 @@ ESAC_HD bool p3p_pose(const float obj[4][3], const float img[4][2], double f, do
     return true;
 }
 
-// Float rejection prefilter for a sampling try.  Returns false only when the try is certain to fail the
-// 4-point gate (every P3P root reprojects the 4th point farther than `margin` times the inlier threshold and no
-// numerical decision was borderline); true means "run the exact fp64 path".  Never the final word on accept.
-ESAC_HD bool p3p_may_pass(const float obj[4][3], const float img[4][2], float f, float ppx, float ppy, float tau,
-                          float margin = 4.f) {
-    float y[3][3], x[3][3], x3[3];
-    const float ifx = 1.f / f;
-    for (int i = 0; i < 3; ++i) {
-        float bx = (img[i][0] - ppx) * ifx, by = (img[i][1] - ppy) * ifx;
-        float n = rsqrtf(bx * bx + by * by + 1.f);
-        y[i][0] = bx * n; y[i][1] = by * n; y[i][2] = n;
-        for (int c = 0; c < 3; ++c) x[i][c] = obj[i][c] - obj[0][c];  // recentre: float differences of float inputs
-    }
-    for (int c = 0; c < 3; ++c) x3[c] = obj[3][c] - obj[0][c];
-    float lam[4][3], amax, cs[3], ss[3];
-    bool unc;
-    int n = p3p_lambdas<float>(y, x, lam, amax, cs, ss, unc);
-    if (unc || !(amax == amax)) return true;
-    if (n == 0) return false;
-    // 4th point in the (non-orthogonal) frame of the scene triangle: x3 = x0 + al*d1 + be*d2 + ga*(d1 x d2).
-    // A rigid motion maps that frame onto the camera-side triangle's, so no rotation has to be built per root.
-    const float* d1 = x[1];
-    const float* d2 = x[2];  // x[0] is the origin after recentring
-    float nrm[3];
-    cross3(d1, d2, nrm);
-    const float g11 = d1[0] * d1[0] + d1[1] * d1[1] + d1[2] * d1[2], g12 = d1[0] * d2[0] + d1[1] * d2[1] + d1[2] * d2[2];
-    const float g22 = d2[0] * d2[0] + d2[1] * d2[1] + d2[2] * d2[2], nn = nrm[0] * nrm[0] + nrm[1] * nrm[1] + nrm[2] * nrm[2];
-    const float det = g11 * g22 - g12 * g12;
-    if (!(det > 1e-6f * g11 * g22) || !(nn > 0.f)) return true;  // nearly collinear scene triangle: exact path decides
-    const float v1 = x3[0] * d1[0] + x3[1] * d1[1] + x3[2] * d1[2], v2 = x3[0] * d2[0] + x3[1] * d2[1] + x3[2] * d2[2];
-    const float idet = Num<float>::div_(1.f, det);
-    const float al = (v1 * g22 - v2 * g12) * idet, be = (v2 * g11 - v1 * g12) * idet;
-    const float ga = Num<float>::div_(x3[0] * nrm[0] + x3[1] * nrm[1] + x3[2] * nrm[2], nn);
-    const float lim = margin * tau, lim2 = lim * lim;
-    const float sa = Num<float>::sqrt_(amax);
-#pragma unroll 1
-    for (int s = 0; s < n; ++s) {
-        float P0[3], e1[3], e2[3], m[3];
-        for (int c = 0; c < 3; ++c) {
-            P0[c] = lam[s][0] * sa * y[0][c];
-            e1[c] = lam[s][1] * sa * y[1][c] - P0[c];
-            e2[c] = lam[s][2] * sa * y[2][c] - P0[c];
-        }
-        cross3(e1, e2, m);
-        const float xc = P0[0] + al * e1[0] + be * e2[0] + ga * m[0];
-        const float yc = P0[1] + al * e1[1] + be * e2[1] + ga * m[1];
-        const float zc = P0[2] + al * e1[2] + be * e2[2] + ga * m[2];
-        const float iz = Num<float>::div_(1.f, zc);
-        const float du = ppx + f * xc * iz - img[3][0], dv = ppy + f * yc * iz - img[3][1];
-        const float e = du * du + dv * dv;
-        if (!(e > lim2)) return true;  // close enough (or NaN/inf): let the exact path decide
-    }
-    return false;
-}
-
 // The reference's 4-point gate (esac_util.h:202-223): every minimal-set point must reproject within
 // the inlier threshold, measured on float-rounded projections.
 ESAC_HD bool minimal_set_gate(const float obj[4][3], const float img[4][2], const Pose& pose, double f,

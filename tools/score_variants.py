@@ -1,6 +1,6 @@
 """Times the scoring kernel for different launch shapes on the bench workload (GPU only)."""
 import sys, json
-sys.path.insert(0, '/root/repo')
+sys.path.insert(0, str(__import__('pathlib').Path(__file__).resolve().parents[1]))
 import numpy as np, torch
 import esac_b200.api as api
 from esac_b200.synth import make_scene
