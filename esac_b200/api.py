@@ -34,6 +34,7 @@ class Stats(C.Structure):
 
 
 _lib = None
+EXCHANGE_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_int, C.POINTER(C.c_double), C.c_int)
 
 
 def load_library() -> C.CDLL:
@@ -61,6 +62,9 @@ def load_library() -> C.CDLL:
     lib.esacb200_backward.argtypes = [vp, vp, vp, i32, i32, i32, vp, i64, i32, vp, f32, f32, f32] + cam + [C.POINTER(f64)]
     lib.esacb200_forward_batch.argtypes = [vp, i32, vp, i32, i32, i32, vp, i64, i32, vp] + cam + [vp]
     lib.esacb200_forward_batch.restype = i32
+    lib.esacb200_backward_sharded.argtypes = ([vp, vp, vp, i32, i32, i32, vp, i64, i32, vp, f32, f32, f32] + cam +
+                                               [EXCHANGE_FN, vp, C.POINTER(f64)])
+    lib.esacb200_backward_sharded.restype = i32
     lib.esacb200_score_poses.argtypes = [vp, vp, i32, i32, i32, vp, i64, i32, vp] + cam + [vp]
     lib.esacb200_refine_poses.argtypes = [vp, vp, i32, i32, i32, vp, i64, i32, vp, i32, i32, f32, f32, f32, f32, f32, i32, vp, vp]
     lib.esacb200_get_stats.argtypes = [vp, C.POINTER(Stats)]
@@ -338,6 +342,50 @@ def backward(sceneCoordinates, outGradients, hypAssignment, gtPose, wLossRot, wL
                                         float(wLossTrans), float(lossCut), int(shiftX), int(shiftY), float(focalLength),
                                         float(ppointX), float(ppointY), float(inlierThreshold), float(inlierAlpha),
                                         float(inlierBeta), float(maxReproj), int(subSampling), C.byref(loss)))
+    gr.finish()
+    return float(loss.value)
+
+
+def backward_sharded(sceneCoordinates, outGradients, hypAssignment, gtPose, wLossRot, wLossTrans, lossCut, shiftX, shiftY,
+                     focalLength, ppointX, ppointY, inlierThreshold, inlierAlpha, inlierBeta, maxReproj, subSampling,
+                     exchange, hyp_offset=0) -> float:
+    """esac.backward on this rank's shard of the experts / hypotheses.  `exchange(phase, values) -> list` performs the two
+    cross-rank reductions (see include/esac_b200.h); returns the GLOBAL expected loss."""
+    _check(sceneCoordinates, "Float", 4, "sceneCoordinates")
+    _check(outGradients, "Float", 4, "outGradients")
+    _check(hypAssignment, "Long", 1, "hypAssignment")
+    _check(gtPose, "Float", 2, "gtPose")
+    co = _Arg(sceneCoordinates)
+    gr = _Arg(outGradients, writable=True)
+    gt = _Arg(gtPose)
+    aptr, astride, M, adev, _keep = _assign_arg(hypAssignment)
+    ctx = _pick_ctx(co.device, gr.device, gt.device, adev)
+    E, _, H, W = (int(s) for s in sceneCoordinates.shape)
+    err = []
+
+    def _cb(user, phase, values, n):
+        try:
+            out = exchange(int(phase), [values[i] for i in range(n)])
+            for i in range(n):
+                values[i] = float(out[i])
+            return 0
+        except Exception as e:  # never let an exception cross the C boundary
+            err.append(e)
+            return 1
+
+    cb = EXCHANGE_FN(_cb)
+    loss = C.c_double(0.0)
+    ctx.set_option("hyp_offset", hyp_offset)
+    try:
+        rc = ctx.lib.esacb200_backward_sharded(ctx.handle, co.ptr, gr.ptr, E, H, W, aptr, astride, M, gt.ptr, float(wLossRot),
+                                               float(wLossTrans), float(lossCut), int(shiftX), int(shiftY), float(focalLength),
+                                               float(ppointX), float(ppointY), float(inlierThreshold), float(inlierAlpha),
+                                               float(inlierBeta), float(maxReproj), int(subSampling), cb, None, C.byref(loss))
+    finally:
+        ctx.set_option("hyp_offset", 0)
+    if err:
+        raise err[0]
+    ctx.check(rc)
     gr.finish()
     return float(loss.value)
 

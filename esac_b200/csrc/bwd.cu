@@ -87,8 +87,8 @@ __global__ void __launch_bounds__(1024) bwd_loss_kernel(const __grid_constant__ 
     if (tid == 0) {
         double s = 0;
         for (int h = 0; h < P.M; ++h) s += a.probs[h] * a.losses[h];  // esac.cpp:357-362 order
-        expected = s;
-        *a.out_loss = s;
+        *a.out_loss = s;                                              // local (this rank's) part of the expectation
+        expected = a.expected_override ? *a.expected_override : s;    // multi-GPU: sum over all ranks
     }
     __syncthreads();
     const int nc = *a.n_contrib;
@@ -412,6 +412,15 @@ __global__ void __launch_bounds__(kBwdThreads) bwd_assemble_kernel(const __grid_
         o2 = (float)((double)o2 + (sg.p * h2 + g2));
     }
     if (live) { gr[p] = o0; gr[P.N + p] = o1; gr[2 * (size_t)P.N + p] = o2; }
+}
+
+void launch_backward_losses(const BwdArgs& a, cudaStream_t st) {
+    BwdAux x;
+    x.hg = (HypGrad*)a.hyp_grad;
+    x.red = a.red;
+    x.expert_njobs = (int*)a.job_of;
+    x.tiles = bwd_tiles(a.P.N);
+    bwd_loss_kernel<<<1, 1024, 0, st>>>(a, x);
 }
 
 void launch_backward(const BwdArgs& a, int max_jobs, cudaStream_t st) {

@@ -62,6 +62,7 @@ struct esacb200_ctx {
     int fixed_seed = 0;
     int refine_group_opt = 0;
     int sample_prefilter = 1;
+    int hyp_offset = 0;
     int score_ppt_opt = 0, score_hc_opt = 0;
     int refine_coresident = 0;
     char err[512] = {0};
@@ -246,7 +247,7 @@ int run_sample(esacb200_ctx* ctx, const Plan& pl, uint64_t seed) {
     st.M = P.M;
     CK(ctx->coords4.ensure((size_t)P.E * P.N * sizeof(float4)));
     ctx->st.kernel_launches += launch_sample(pl.d_coords, ctx->coords4.as<float4>(), ctx->assign32.as<int>(), P, seed, ctx->max_tries,
-                                             ctx->inj_M ? ctx->inject.as<int>() : nullptr, ctx->inj_T, st, ctx->sm_count, ctx->sample_prefilter,
+                                             ctx->inj_M ? ctx->inject.as<int>() : nullptr, ctx->inj_T, st, ctx->sm_count, ctx->sample_prefilter, ctx->hyp_offset,
                                              ctx->poses.as<Pose>(), ctx->cells.as<int>(), ctx->tries.as<int>(), ctx->stream);
     CK(cudaGetLastError());
     mark(ctx, EV_SAMPLE);
@@ -462,6 +463,7 @@ int esacb200_set_option(esacb200_ctx* ctx, const char* key, double v) {
     else if (!strcmp(key, "fixed_seed")) ctx->fixed_seed = v != 0;
     else if (!strcmp(key, "refine_group")) ctx->refine_group_opt = (int)v;
     else if (!strcmp(key, "sample_prefilter")) ctx->sample_prefilter = v != 0;
+    else if (!strcmp(key, "hyp_offset")) ctx->hyp_offset = (int)v;  // global index of local hypothesis 0 (sharded runs)
     else if (!strcmp(key, "score_ppt")) ctx->score_ppt_opt = (int)v;   // 0 = automatic, else 2 / 4 / 8 cells per thread
     else if (!strcmp(key, "score_hc")) ctx->score_hc_opt = (int)v;     // 0 = automatic, else hypotheses per chunk (<= 64)
     else return fail(ctx, ESACB200_ERR_ARG, "unknown option '%s'", key);
@@ -680,10 +682,10 @@ int esacb200_refine_poses(esacb200_ctx* ctx, const float* coords, int E, int H, 
 
 
 // -------------------------------------------------------------------------------------------------
-int esacb200_backward(esacb200_ctx* ctx, const float* coords, float* grads, int E, int H, int W, const int64_t* assign,
-                      int64_t assign_stride, int M, const float* gt_pose, float wRot, float wTrans, float cut, int shiftX,
-                      int shiftY, float f, float ppx, float ppy, float tau, float alpha, float beta, float maxReproj, int sub,
-                      double* out_loss) {
+static int backward_impl(esacb200_ctx* ctx, const float* coords, float* grads, int E, int H, int W, const int64_t* assign,
+                         int64_t assign_stride, int M, const float* gt_pose, float wRot, float wTrans, float cut, int shiftX,
+                         int shiftY, float f, float ppx, float ppy, float tau, float alpha, float beta, float maxReproj, int sub,
+                         esacb200_exchange_fn exchange, void* user, double* out_loss) {
     if (!ctx) return ESACB200_ERR_ARG;
     if (!coords || !assign || !grads || !gt_pose) return fail(ctx, ESACB200_ERR_ARG, "null pointer argument");
     Plan pl;
@@ -709,6 +711,16 @@ int esacb200_backward(esacb200_ctx* ctx, const float* coords, float* grads, int 
     if (rc) return rc;
     rc = run_score(ctx, pl);
     if (rc) return rc;
+    if (exchange) {
+        // exchange 1: softmax normalisation over the hypotheses of ALL ranks
+        CK(cudaMemcpyAsync(ctx->h_dbl, ctx->stats.as<double>() + 5, 2 * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+        CK(cudaStreamSynchronize(ctx->stream));
+        double v[2] = {ctx->h_dbl[0], ctx->h_dbl[1]};
+        if (exchange(user, 1, v, 2) != 0) return fail(ctx, ESACB200_ERR_ARG, "exchange callback failed (phase 1)");
+        launch_rescale_probs(ctx->scores.as<double>(), P, v[0], v[1], ctx->probs.as<double>(), ctx->contrib.as<int>(),
+                             sc + S_NCONTRIB, ctx->stream);
+        ctx->st.kernel_launches += 1;
+    }
     // refHyps = initHyps for everything below PROB_THRESH (esac.cpp:331-334)
     CK(cudaMemcpyAsync(ctx->poses_ref.p, ctx->poses.p, (size_t)M * sizeof(Pose), cudaMemcpyDeviceToDevice, ctx->stream));
     // Refining many hypotheses is fp64-throughput bound, so every SM should be busy and no CTA should wait at an inter-CTA
@@ -757,6 +769,21 @@ int esacb200_backward(esacb200_ctx* ctx, const float* coords, float* grads, int 
     }
     b.wRot = wRot; b.wTrans = wTrans; b.cut = cut;
     b.P = P;
+    b.expected_override = nullptr;
+    double global_loss = 0;
+    if (exchange) {
+        // exchange 2: the expectation sum_h p_h loss_h runs over the hypotheses of all ranks (esac.cpp:357-362, esac_derivative.h:372-374)
+        launch_backward_losses(b, ctx->stream);
+        CK(cudaMemcpyAsync(ctx->h_dbl, ctx->stats.as<double>() + 4, sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+        CK(cudaStreamSynchronize(ctx->stream));
+        double v[1] = {ctx->h_dbl[0]};
+        if (exchange(user, 2, v, 1) != 0) return fail(ctx, ESACB200_ERR_ARG, "exchange callback failed (phase 2)");
+        global_loss = v[0];
+        ctx->h_dbl[6] = v[0];
+        CK(cudaMemcpyAsync(ctx->stats.as<double>() + 7, ctx->h_dbl + 6, sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+        b.expected_override = ctx->stats.as<double>() + 7;
+        ctx->st.kernel_launches += 1;
+    }
     launch_backward(b, M, ctx->stream);
     CK(cudaGetLastError());
     ctx->st.kernel_launches += 5;
@@ -769,17 +796,34 @@ int esacb200_backward(esacb200_ctx* ctx, const float* coords, float* grads, int 
     CK(cudaGetLastError());
     const int* hs = (const int*)(ctx->h_out + 20);
     if (hs[S_FLAGS]) return fail(ctx, ESACB200_ERR_ARG, "hypAssignment holds an expert index outside [0, %d)", E);
-    if (out_loss) *out_loss = ctx->h_dbl[4];
+    if (out_loss) *out_loss = exchange ? global_loss : ctx->h_dbl[4];
     ctx->st.M = M;
     ctx->st.winner = hs[S_WINNER];
     ctx->st.n_contrib = hs[S_NCONTRIB];
     ctx->st.entropy = ctx->h_dbl[0];
-    ctx->st.expected_loss = ctx->h_dbl[4];
+    ctx->st.expected_loss = exchange ? global_loss : ctx->h_dbl[4];
     ctx->last_M = M;
     ctx->last_backward = true;
     finish_stats(ctx);
     ctx->inj_M = ctx->inj_T = 0;
     return ESACB200_OK;
+}
+
+int esacb200_backward(esacb200_ctx* ctx, const float* coords, float* grads, int E, int H, int W, const int64_t* assign,
+                      int64_t assign_stride, int M, const float* gt_pose, float wRot, float wTrans, float cut, int shiftX,
+                      int shiftY, float f, float ppx, float ppy, float tau, float alpha, float beta, float maxReproj, int sub,
+                      double* out_loss) {
+    return backward_impl(ctx, coords, grads, E, H, W, assign, assign_stride, M, gt_pose, wRot, wTrans, cut, shiftX, shiftY, f, ppx,
+                         ppy, tau, alpha, beta, maxReproj, sub, nullptr, nullptr, out_loss);
+}
+
+int esacb200_backward_sharded(esacb200_ctx* ctx, const float* coords, float* grads, int E, int H, int W, const int64_t* assign,
+                              int64_t assign_stride, int M, const float* gt_pose, float wRot, float wTrans, float cut,
+                              int shiftX, int shiftY, float f, float ppx, float ppy, float tau, float alpha, float beta,
+                              float maxReproj, int sub, esacb200_exchange_fn exchange, void* user, double* out_loss) {
+    if (!exchange) return ctx ? fail(ctx, ESACB200_ERR_ARG, "exchange callback is null") : ESACB200_ERR_ARG;
+    return backward_impl(ctx, coords, grads, E, H, W, assign, assign_stride, M, gt_pose, wRot, wTrans, cut, shiftX, shiftY, f, ppx,
+                         ppy, tau, alpha, beta, maxReproj, sub, exchange, user, out_loss);
 }
 
 int esacb200_copy_last_scores(esacb200_ctx* ctx, double* dst, int M) {

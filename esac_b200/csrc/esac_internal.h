@@ -86,6 +86,9 @@ void launch_select(const float* part, const int* slot_of, const Problem& P, int 
                    double* stats /* [0]=entropy [1]=winner [2]=n_contrib */, int* winner, int* contrib,
                    int* n_contrib, cudaStream_t st);
 
+void launch_rescale_probs(const double* scores, const Problem& P, double gmax, double gsum, double* probs, int* contrib,
+                          int* n_contrib, cudaStream_t st);
+
 // --- hyp.cu -------------------------------------------------------------------------------
 // Work state of the sampling waves (all device memory, M = hypotheses).
 struct Accepted {
@@ -106,8 +109,8 @@ struct SampleState {
 };
 // Returns the number of kernel launches it enqueued.
 int launch_sample(const float* coords, float4* coords4, const int* assign32, const Problem& P, uint64_t seed, int max_tries,
-                  const int* injected, int inj_T, const SampleState& st, int sm_count, int use_prefilter, Pose* poses, int* cells,
-                  int* tries, cudaStream_t st_);
+                  const int* injected, int inj_T, const SampleState& st, int sm_count, int use_prefilter, int hyp_offset,
+                  Pose* poses, int* cells, int* tries, cudaStream_t st_);
 
 // --- refine.cu ----------------------------------------------------------------------------
 // Refines poses_in[jobs[j]] -> poses_out[jobs[j]] for j < *n_jobs (device scalar) or n_jobs_host.
@@ -162,8 +165,11 @@ struct BwdArgs {
     float gt[16];
     float wRot, wTrans, cut;
     Problem P;
+    const double* expected_override;  // device scalar: global expected loss (multi-GPU), or null
 };
 void launch_backward(const BwdArgs& a, int max_jobs, cudaStream_t st);
+// phase split for the multi-GPU path: losses + local expectation only / everything after the loss exchange
+void launch_backward_losses(const BwdArgs& a, cudaStream_t st);
 size_t bwd_hypgrad_bytes();
 int bwd_red_vals();
 int bwd_tiles(int N);

@@ -40,6 +40,7 @@ struct SampleArgs {
     const int* injected;  // [M][inj_T][4][2] or null
     int inj_T;
     int use_prefilter;    // 0: every try goes to the exact path (self-check of the prefilter)
+    int hyp_offset;       // global index of local hypothesis 0 (multi-GPU shards draw the stream of the unsharded problem)
     SampleState st;
 };
 
@@ -49,7 +50,7 @@ __device__ __forceinline__ void load_try(const SampleArgs& a, int h, int t, int 
         const int* c = a.injected + ((size_t)h * a.inj_T + t) * 8;
         for (int j = 0; j < 4; ++j) { cx[j] = c[2 * j]; cy[j] = c[2 * j + 1]; }
     } else {
-        draw_minimal_set(a.seed, (uint32_t)h, (uint32_t)t, P.W, P.H, cx, cy);
+        draw_minimal_set(a.seed, (uint32_t)(h + a.hyp_offset), (uint32_t)t, P.W, P.H, cx, cy);
     }
     const float4* pl = a.coords4 + (size_t)a.assign32[h] * P.N;
     for (int j = 0; j < 4; ++j) {
@@ -243,12 +244,12 @@ __global__ void __launch_bounds__(64) emit_kernel(const __grid_constant__ Sample
 }
 
 int launch_sample(const float* coords, float4* coords4, const int* assign32, const Problem& P, uint64_t seed, int max_tries,
-                  const int* injected, int inj_T, const SampleState& st, int sm_count, int use_prefilter, Pose* poses, int* cells,
-                  int* tries, cudaStream_t stream) {
+                  const int* injected, int inj_T, const SampleState& st, int sm_count, int use_prefilter, int hyp_offset,
+                  Pose* poses, int* cells, int* tries, cudaStream_t stream) {
     SampleArgs a;
     a.coords4 = coords4; a.assign32 = assign32; a.P = P; a.seed = seed;
     a.limit = injected ? (max_tries < inj_T ? max_tries : inj_T) : max_tries;
-    a.injected = injected; a.inj_T = inj_T; a.st = st; a.use_prefilter = use_prefilter;
+    a.injected = injected; a.inj_T = inj_T; a.st = st; a.use_prefilter = use_prefilter; a.hyp_offset = hyp_offset;
     int launches = 0;
     interleave_kernel<<<sm_count * 8, 256, 0, stream>>>(coords, coords4, P.E, P.N); ++launches;
     sample_init_kernel<<<(P.M + 255) / 256, 256, 0, stream>>>(st, P.M); ++launches;

@@ -524,6 +524,7 @@ __global__ void __launch_bounds__(1024) select_kernel(const float* __restrict__ 
         if (i == 0x7fffffff) i = 0;
         *winner = i;
         stats[0] = en; stats[1] = (double)i;
+        stats[5] = mx; stats[6] = sum;  // local softmax normalisation, for the multi-GPU exchange
         srun = 0;
     }
     __syncthreads();
@@ -548,6 +549,42 @@ void launch_select(const float* part, const int* slot_of, const Problem& P, int 
                    double* stats, int* winner, int* contrib, int* n_contrib, cudaStream_t st) {
     finish_scores_kernel<<<(P.M * 32 + 255) / 256, 256, 0, st>>>(part, slot_of, P, T, scores);
     select_kernel<<<1, 1024, 0, st>>>(part, slot_of, P, T, scores, probs, stats, winner, contrib, n_contrib);
+}
+
+
+// Multi-GPU backward: hypothesis probabilities w.r.t. the GLOBAL softmax normalisation (max and sum of exp over all
+// ranks, exchanged by the host), and the ordered list of contributing hypotheses rebuilt from them.
+__global__ void __launch_bounds__(1024) rescale_probs_kernel(const double* __restrict__ scores, Problem P, double gmax, double gsum,
+                                                             double* probs, int* contrib, int* n_contrib) {
+    __shared__ int swc[32];
+    __shared__ int srun;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nw = blockDim.x >> 5;
+    if (tid == 0) srun = 0;
+    __syncthreads();
+    for (int b = 0; b < P.M; b += blockDim.x) {
+        const int h = b + tid;
+        bool flag = false;
+        if (h < P.M) {
+            const double p = exp(scores[h] - gmax) / gsum;
+            probs[h] = p;
+            flag = !(p < kProbThresh);
+        }
+        const unsigned m = __ballot_sync(0xffffffffu, flag);
+        if (lane == 0) swc[warp] = __popc(m);
+        __syncthreads();
+        int off = srun;
+        for (int w = 0; w < warp; ++w) off += swc[w];
+        if (flag) contrib[off + __popc(m & ((1u << lane) - 1u))] = h;
+        __syncthreads();
+        if (tid == 0) { int t = 0; for (int w = 0; w < nw; ++w) t += swc[w]; srun += t; }
+        __syncthreads();
+    }
+    if (tid == 0) *n_contrib = srun;
+}
+
+void launch_rescale_probs(const double* scores, const Problem& P, double gmax, double gsum, double* probs, int* contrib,
+                          int* n_contrib, cudaStream_t st) {
+    rescale_probs_kernel<<<1, 1024, 0, st>>>(scores, P, gmax, gsum, probs, contrib, n_contrib);
 }
 
 }  // namespace esacb200

@@ -41,7 +41,42 @@ def select_global(gathered: np.ndarray, M_local: int):
     return winner, rank, pose, expert, probs
 
 
-def forward_sharded(coords_local, assign_local, out_pose, params, expert_offset: int, group=None, local_forward=None):
+def make_exchange(group=None, device=None):
+    """The two reductions of the sharded backward as torch.distributed collectives (NCCL on `device`, gloo on CPU):
+    phase 1 all-gathers (max, sum exp) pairs and merges them into the global softmax normalisation, phase 2 sums the
+    partial expectations."""
+    import torch
+    import torch.distributed as dist
+
+    def exchange(phase, values):
+        world = dist.get_world_size(group)
+        t = torch.tensor(values, dtype=torch.float64, device=device)
+        if phase == 1:
+            g = torch.empty(world * 2, dtype=torch.float64, device=device)
+            dist.all_gather_into_tensor(g, t, group=group)
+            g = g.view(world, 2).cpu().numpy()
+            gmax = float(g[:, 0].max())
+            gsum = float((g[:, 1] * np.exp(g[:, 0] - gmax)).sum())
+            return [gmax, gsum]
+        dist.all_reduce(t, op=dist.ReduceOp.SUM, group=group)
+        return [float(v) for v in t.cpu()]
+
+    return exchange
+
+
+def backward_sharded(coords_local, grads_local, assign_local, gt_pose, w_rot, w_trans, cut, params, hyp_offset: int, group=None):
+    """esac.backward with experts sharded expert-major across ranks: every rank owns its experts' planes and gradient
+    slices (no gradient reduction); two KB-sized collectives give every rank the global softmax and the global expected
+    loss, which it returns.  `hyp_offset` = number of hypotheses owned by lower ranks."""
+    from . import api
+    dev = coords_local.device if getattr(coords_local, "is_cuda", False) else None
+    ex = make_exchange(group, dev)
+    return api.backward_sharded(coords_local, grads_local, assign_local, gt_pose, w_rot, w_trans, cut, *params, exchange=ex,
+                                hyp_offset=hyp_offset)
+
+
+def forward_sharded(coords_local, assign_local, out_pose, params, expert_offset: int, group=None, local_forward=None,
+                    hyp_offset: int = 0):
     """esac.forward over experts sharded across the ranks of `group`.  coords_local [E_local,3,H,W] and
     assign_local [M_local] (expert indices local to the shard) live on this rank; out_pose [4,4] receives the
     global winner's camera pose on every rank; returns the global expert index."""
@@ -53,8 +88,12 @@ def forward_sharded(coords_local, assign_local, out_pose, params, expert_offset:
     if local_forward is None:
         dev = coords_local.device if coords_local.is_cuda else torch.device("cuda", torch.cuda.current_device())
         pose = torch.zeros(4, 4, device=dev)
-        e_local = api.forward(coords_local, assign_local, pose, *params)
         ctx = api.context(dev.index)
+        ctx.set_option("hyp_offset", hyp_offset)
+        try:
+            e_local = api.forward(coords_local, assign_local, pose, *params)
+        finally:
+            ctx.set_option("hyp_offset", 0)
         scores = torch.empty(M, dtype=torch.float64, device=dev)
         ctx.copy_last_scores(scores)
         st = ctx.stats()

@@ -49,7 +49,8 @@ int esacb200_set_seed(esacb200_ctx* ctx, uint64_t seed);
 /* Options: "max_tries" (esac.cpp:44 MAX_SAMPLING_TRIES, default 1000000), "max_ref_steps"
  * (esac.cpp:45 MAX_REF_STEPS, default 100), "fixed_seed" (1: do not advance the call counter),
  * "refine_group" (CTAs per refinement job, 0 = automatic), "sample_prefilter" (default 1; 0 sends every sampling
- * try through the exact fp64 path -- the results must not change, only the time). */
+ * try through the exact fp64 path -- the results must not change, only the time), "hyp_offset" (global index of
+ * local hypothesis 0 for the minimal-set stream; sharded runs), "score_ppt" / "score_hc" (scoring launch shape). */
 int esacb200_set_option(esacb200_ctx* ctx, const char* key, double value);
 /* Inject minimal sets instead of drawing them: cells int32 [M][T][4][2] (x, y), host pointer,
  * copied; T candidate sets per hypothesis tried in order.  NULL clears.  Applies to the next call. */
@@ -74,6 +75,20 @@ int esacb200_backward(esacb200_ctx* ctx, const float* coords, float* grads, int 
                       int subSampling, double* out_loss);
 
 /* ---- additive entry points ------------------------------------------------------------------ */
+/* esac_backward over hypotheses sharded across processes (one per GPU; experts expert-major, so gradient slices are
+ * disjoint).  The path has two exchange steps; the library calls `exchange` on the host at each:
+ *   phase 1: values = {local max score, local sum exp(score - local max)}  -> replace by the GLOBAL {max, sum exp(score - max)}
+ *   phase 2: values = {local sum_h p_h loss_h}                               -> replace by the sum over all ranks
+ * (return 0 on success).  The caller implements them with its collective of choice (esac_b200/sharded.py: NCCL
+ * all-gather / all-reduce through torch.distributed).  *out_loss = the global expected loss.  Set option "hyp_offset" to
+ * the global index of this shard's first hypothesis so that the shards draw the minimal sets of the unsharded problem. */
+typedef int (*esacb200_exchange_fn)(void* user, int phase, double* values, int n);
+int esacb200_backward_sharded(esacb200_ctx* ctx, const float* coords, float* grads, int E, int H, int W,
+                              const int64_t* assign, int64_t assign_stride, int M, const float* gt_pose, float wLossRot,
+                              float wLossTrans, float lossCut, int shiftX, int shiftY, float focalLength, float ppointX,
+                              float ppointY, float inlierThreshold, float inlierAlpha, float inlierBeta, float maxReproj,
+                              int subSampling, esacb200_exchange_fn exchange, void* user, double* out_loss);
+
 /* esac_forward over B images of one shape (the reference's callers loop with batch_size=1, test_esac.py:137):
  * coords float32 [B,E,3,H,W], assign int64 [B,M] (rows contiguous, element stride assign_stride; 0 = one expert for all),
  * out_poses float32 [B,4,4], out_experts int [B] (host).  One host synchronisation for the whole batch; host maps are

@@ -1,0 +1,89 @@
+"""Two-GPU identity tests (skipped on a single-GPU box): experts sharded expert-major over 2 ranks must reproduce the
+single-GPU result -- same winner / pose in forward (one all-gather of scores), same expected loss and the same gradient
+slices in backward (two KB-sized exchanges)."""
+import os
+import socket
+
+import numpy as np
+import pytest
+import torch
+
+from esac_b200.synth import make_scene
+
+pytestmark = pytest.mark.gpu
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _worker(rank, world, port, q):
+    import torch.distributed as dist
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    import esac_b200.api as api
+    from esac_b200 import sharded
+    E, Mper = 4, 24
+    sc = make_scene(E=E, H=30, W=40, M=Mper, sub=8, seed=77, per_expert=True, active_only=False)
+    Eloc = E // world
+    e0 = rank * Eloc
+    hsel = slice(e0 * Mper, (e0 + Eloc) * Mper)
+    dev = torch.device("cuda", rank)
+    coords_l = torch.from_numpy(sc.coords[e0:e0 + Eloc]).to(dev)
+    assign_l = torch.from_numpy(sc.assign[hsel] - e0).to(dev)
+    ctx = api.context(rank)
+    ctx.set_option("fixed_seed", 1)
+    # ---- forward ----
+    ctx.set_seed(5)
+    out = torch.zeros(4, 4, device=dev)
+    e = sharded.forward_sharded(coords_l, assign_l, out, sc.params, expert_offset=e0, hyp_offset=e0 * Mper)
+    # ---- backward ----
+    ctx.set_seed(5)
+    grads_l = torch.zeros_like(coords_l)
+    loss = sharded.backward_sharded(coords_l, grads_l, assign_l, torch.from_numpy(sc.gt_pose), 1.0, 100.0, 100.0, sc.params,
+                                    hyp_offset=e0 * Mper)
+    res = {"rank": rank, "expert": e, "pose": out.cpu().numpy(), "loss": loss, "grads": grads_l.cpu().numpy()}
+    if rank == 0:  # the unsharded problem on one GPU
+        ctx.set_seed(5)
+        ref_out = np.zeros((4, 4), np.float32)
+        ref_e = api.forward(sc.coords, sc.assign, ref_out, *sc.params)
+        ctx.set_seed(5)
+        g = np.zeros_like(sc.coords)
+        ref_loss = api.backward(sc.coords, g, sc.assign, sc.gt_pose, 1.0, 100.0, 100.0, *sc.params)
+        res.update(ref_expert=ref_e, ref_pose=ref_out, ref_loss=ref_loss, ref_grads=g)
+    q.put(res)
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs (gpurun --gpus 2)")
+def test_two_gpu_sharding_reproduces_single_gpu():
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    ps = [ctx.Process(target=_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in ps:
+        p.start()
+    res = {}
+    for _ in range(2):
+        r = q.get(timeout=300)
+        res[r["rank"]] = r
+    for p in ps:
+        p.join(timeout=120)
+        assert p.exitcode == 0
+    ref = res[0]
+    for r in (0, 1):
+        assert res[r]["expert"] == ref["ref_expert"]
+        assert np.allclose(res[r]["pose"], ref["ref_pose"], atol=1e-6)
+        assert abs(res[r]["loss"] - ref["ref_loss"]) < 1e-9 * max(1.0, abs(ref["ref_loss"]))
+        sl = slice(2 * r, 2 * r + 2)
+        scale = max(np.abs(ref["ref_grads"]).max(), 1e-12)
+        assert np.abs(res[r]["grads"] - ref["ref_grads"][sl]).max() / scale < 1e-6
+    assert np.abs(ref["ref_grads"]).max() > 0

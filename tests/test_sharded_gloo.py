@@ -70,3 +70,35 @@ def test_forward_sharded_world2_gloo():
     for rank, e, pose in res:
         assert e == 1 * 3 + 2          # rank 1's shard, local expert 2
         assert np.allclose(pose, np.eye(4) * 2)
+
+
+def _exchange_worker(rank, world, port, q):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    ex = sharded.make_exchange()
+    scores = np.array([[3.0, 7.0, 1.0], [9.0, 2.0, 8.5]])[rank]
+    mx = scores.max()
+    g = ex(1, [mx, np.exp(scores - mx).sum()])
+    tot = ex(2, [float(rank + 1) * 0.25])
+    q.put((rank, g, tot))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_backward_exchange_world2_gloo():
+    """The two reductions of the sharded backward (global softmax normalisation, global expected loss)."""
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    ps = [ctx.Process(target=_exchange_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in ps:
+        p.start()
+    for p in ps:
+        p.join(timeout=240)
+        assert p.exitcode == 0
+    allsc = np.array([3.0, 7.0, 1.0, 9.0, 2.0, 8.5])
+    for _ in range(2):
+        rank, g, tot = q.get(timeout=5)
+        assert abs(g[0] - 9.0) < 1e-15 and abs(g[1] - np.exp(allsc - 9.0).sum()) < 1e-12
+        assert abs(tot[0] - 0.75) < 1e-15
