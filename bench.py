@@ -65,7 +65,7 @@ class ClockSampler:
 
     def start(self):
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "20",
                                           "-i", str(self.index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
@@ -128,16 +128,20 @@ def run_reference(args, rank: int, world: int):
     # bounded sample: `take` hypotheses spread over the experts (every 1792/take-th hypothesis)
     idx = np.linspace(0, len(sc.assign) - 1, take).astype(int)
     sc.assign = sc.assign[idx]
-    for _ in range(args.warmup):
+    # every step is one bounded sample; the number of steps actually run is capped so that the arm ends within minutes
+    # whatever K the driver passes (a step costs seconds of CPU time, the metric is a rate and does not depend on K)
+    warm = min(args.warmup, 3)
+    steps = min(args.steps, 24)
+    for _ in range(warm):
         cpu_reference_run(sc, take, 1)
     t0 = time.perf_counter()
-    for k in range(args.steps):
+    for k in range(steps):
         cpu_reference_run(sc, take, 2 + k)
     dt = time.perf_counter() - t0
-    val = take * args.steps / dt
+    val = take * steps / dt
     cfg = workload_config(args.gpus)
     line = {"impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak",
+            "warmup": args.warmup, "ms_per_step": 1e3 * dt / steps, "steps_run": steps, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f64/f32 mix (OpenCV)", "data": "synthetic", "config": cfg,
             "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": "port",
                              "sample": f"{take} of {E_PER_GPU * HYPS_PER_EXPERT} hypotheses per step, full esac.forward "
@@ -150,8 +154,8 @@ def run_reference(args, rank: int, world: int):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
-    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
@@ -168,6 +172,7 @@ def main():
         raise SystemExit("bench.py needs a CUDA device: this implementation has no CPU path")
     torch.cuda.set_device(local_rank)
     if world > 1:
+        os.environ["NCCL_DEBUG"] = "WARN"  # keep NCCL's version banner off stdout: rank 0 prints exactly one JSON line
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     import esac

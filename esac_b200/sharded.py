@@ -16,13 +16,8 @@ import numpy as np
 def pack_local(scores, pose16, expert_global: int, local_winner: int):
     """float64 vector [M_local + 18]."""
     import torch
-    M = scores.shape[0]
-    buf = torch.empty(M + 18, dtype=torch.float64, device=scores.device)
-    buf[:M] = scores
-    buf[M:M + 16] = pose16.reshape(16).to(torch.float64)
-    buf[M + 16] = float(expert_global)
-    buf[M + 17] = float(local_winner)
-    return buf
+    tail = torch.tensor([float(expert_global), float(local_winner)], dtype=torch.float64, device=scores.device)
+    return torch.cat([scores.reshape(-1), pose16.reshape(16).to(torch.float64), tail])
 
 
 def select_global(gathered: np.ndarray, M_local: int):
@@ -104,7 +99,16 @@ def forward_sharded(coords_local, assign_local, out_pose, params, expert_offset:
     world = dist.get_world_size(group)
     gathered = torch.empty(world * (M + 18), dtype=torch.float64, device=buf.device)
     dist.all_gather_into_tensor(gathered, buf, group=group)
-    _, _, gpose, expert, _ = select_global(gathered.view(world, M + 18).cpu().numpy(), M)
+    g = gathered.view(world, M + 18)
+    if g.is_cuda:
+        # selection on the device, ONE small read-back: [global argmax | every rank's 18-value tail]
+        w = torch.argmax(g[:, :M].reshape(-1)).to(torch.float64).reshape(1)  # first maximum = draw(training=false)
+        small = torch.cat([w, g[:, M:].reshape(-1)]).cpu().numpy()
+        rank = int(small[0]) // M
+        tail = small[1:].reshape(world, 18)[rank]
+        gpose, expert = tail[:16].reshape(4, 4).astype(np.float32), int(tail[16])
+    else:
+        _, _, gpose, expert, _ = select_global(g.numpy(), M)
     if hasattr(out_pose, "copy_"):
         out_pose.copy_(torch.from_numpy(gpose))
     else:

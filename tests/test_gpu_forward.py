@@ -219,3 +219,52 @@ def test_forward_batch_equals_a_loop_of_forward(api):
     finally:
         api.set_option("fixed_seed", 1)
     assert [s.gt_expert for s in scenes] == ref_e
+
+
+def test_tiny_problem_single_hypothesis(api):
+    """M = 1, E = 1 on an 8x10 map: every reduction degenerates to one element."""
+    sc = make_scene(E=1, H=8, W=10, M=1, sub=8, seed=13, outlier_frac=0.0, noise=0.0)
+    ref = np.zeros((4, 4), np.float32)
+    ref_e, tr = O.forward(sc.coords, sc.assign, ref, *sc.params, seed=3, trace=True)
+    api.set_seed(3)
+    out = np.zeros((4, 4), np.float32)
+    e = api.forward(sc.coords, sc.assign, out, *sc.params)
+    hy = api.last_hypotheses()
+    assert e == ref_e == 0 and hy["tries"].tolist() == [tr.hyps[0].tries]
+    assert abs(hy["scores"][0] - tr.scores[0]) < 1e-4
+    rot, trans = pose_error(out, ref)
+    assert rot < ROT_TOL_DEG and trans < TRANS_TOL_M
+
+
+def test_many_experts_many_hypotheses(api):
+    """E = 50 clusters (the reference's largest ensemble, environments/aachen) and M = 2048 on the native 60x80 map."""
+    sc = make_scene(E=50, H=60, W=80, M=2048, sub=8, seed=14)
+    api.set_seed(8)
+    out = np.zeros((4, 4), np.float32)
+    e = api.forward(sc.coords, sc.assign, out, *sc.params)
+    hy = api.last_hypotheses()
+    assert e == sc.gt_expert and np.isfinite(hy["scores"]).all()
+    # spot-check a handful of scores against the C oracle restatement
+    from oracle.build import c_score
+    idx = np.array([0, 1, 500, 1000, 2047])
+    ref, _ = c_score(sc.coords, sc.assign[idx], hy["poses"][idx], *sc.params)
+    assert np.abs(ref - hy["scores"][idx]).max() < SCORE_TOL
+    rot, trans = pose_error(out, sc.gt_pose)
+    assert rot < 1.0 and trans < 0.05
+
+
+def test_sampling_gives_up_after_max_tries_on_an_empty_plane(api):
+    """Hypotheses assigned to an expert whose plane is all zeros (train_esac.py:121 leaves inactive experts at zero) can
+    never pass the 4-point gate: the loop must stop at MAX_SAMPLING_TRIES with the last try's state (esac_util.h:154)."""
+    sc = make_scene(E=2, H=30, W=40, M=8, sub=8, seed=15)
+    sc.coords[:] = 0.0
+    api.set_option("max_tries", 3000)
+    try:
+        api.set_seed(1)
+        out = np.zeros((4, 4), np.float32)
+        api.forward(sc.coords, sc.assign, out, *sc.params)
+        hy = api.last_hypotheses()
+    finally:
+        api.set_option("max_tries", 1000000)
+    assert hy["tries"].tolist() == [3000] * 8
+    assert np.all(hy["poses"] == 0)  # safeSolvePnP's failure state
