@@ -5,6 +5,7 @@ with ctypes, so the build is four nvcc compiles and one link.
 """
 from __future__ import annotations
 
+import hashlib
 import os
 import subprocess
 import sys
@@ -23,36 +24,45 @@ FLAGS = ["-ccbin", "/usr/bin/g++", "-std=c++17", "-gencode", "arch=compute_100a,
          "-Xcompiler", "-fPIC", "-Xptxas", "-v"]
 
 
-def _stale(target: Path, deps) -> bool:
-    if not target.exists():
-        return True
-    t = target.stat().st_mtime
-    return any(Path(d).stat().st_mtime > t for d in deps)
+def _digest(paths) -> str:
+    """Content hash of the sources (mtimes do not survive the snapshot that carries the tree to the GPU box)."""
+    h = hashlib.sha256(" ".join(FLAGS).encode())
+    for p in paths:
+        h.update(Path(p).name.encode())
+        h.update(Path(p).read_bytes())
+    return h.hexdigest()
 
 
 def build_library(force: bool = False, verbose: bool = False) -> Path:
     OBJ.mkdir(exist_ok=True)
     hdrs = [CSRC / h for h in HEADERS]
+    stamp = HERE / "libesac_b200.so.srchash"
+    want = _digest([CSRC / s for s in SOURCES] + hdrs)
+    if not force and LIB.exists() and stamp.exists() and stamp.read_text().strip() == want:
+        return LIB
 
     def compile_one(src: str):
         s = CSRC / src
         o = OBJ / (src + ".o")
-        if force or _stale(o, [s] + hdrs):
+        ostamp = OBJ / (src + ".srchash")
+        owant = _digest([s] + hdrs)
+        if force or not o.exists() or not ostamp.exists() or ostamp.read_text().strip() != owant:
             r = subprocess.run([NVCC] + FLAGS + ["-c", str(s), "-o", str(o)], capture_output=True, text=True)
             (OBJ / (src + ".log")).write_text(r.stdout + r.stderr)
             if r.returncode != 0:
                 raise RuntimeError(f"nvcc failed on {src}:\n{r.stdout}\n{r.stderr}")
+            ostamp.write_text(owant)
             if verbose:
                 print(r.stderr)
         return o
 
     with ThreadPoolExecutor(max_workers=len(SOURCES)) as ex:
         objs = list(ex.map(compile_one, SOURCES))
-    if force or _stale(LIB, objs):
-        r = subprocess.run([NVCC, "-ccbin", "/usr/bin/g++", "-shared", "-o", str(LIB)] + [str(o) for o in objs] +
-                           ["-lcudart"], capture_output=True, text=True)
-        if r.returncode != 0:
-            raise RuntimeError(f"link failed:\n{r.stdout}\n{r.stderr}")
+    r = subprocess.run([NVCC, "-ccbin", "/usr/bin/g++", "-shared", "-o", str(LIB)] + [str(o) for o in objs] + ["-lcudart"],
+                       capture_output=True, text=True)
+    if r.returncode != 0:
+        raise RuntimeError(f"link failed:\n{r.stdout}\n{r.stderr}")
+    stamp.write_text(want)
     return LIB
 
 

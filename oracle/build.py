@@ -5,6 +5,7 @@ libopencv_core / libopencv_calib3d; only the cv2 Python wheel exists), so there 
 from __future__ import annotations
 
 import ctypes as C
+import hashlib
 import subprocess
 from pathlib import Path
 
@@ -15,11 +16,14 @@ OUT = HERE / "_build" / "libesac_oracle.so"
 
 def build_oracle(force: bool = False) -> Path:
     OUT.parent.mkdir(exist_ok=True)
-    if force or not OUT.exists() or OUT.stat().st_mtime < SRC.stat().st_mtime:
+    stamp = OUT.parent / "libesac_oracle.so.srchash"
+    want = hashlib.sha256(SRC.read_bytes()).hexdigest()
+    if force or not OUT.exists() or not stamp.exists() or stamp.read_text().strip() != want:
         cmd = ["/usr/bin/gcc", "-O3", "-fopenmp", "-ffp-contract=off", "-shared", "-fPIC", "-o", str(OUT), str(SRC), "-lm"]
         r = subprocess.run(cmd, capture_output=True, text=True)
         if r.returncode != 0:
             raise RuntimeError(f"gcc failed:\n{r.stdout}\n{r.stderr}")
+        stamp.write_text(want)
     return OUT
 
 

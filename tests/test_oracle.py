@@ -96,3 +96,47 @@ def test_golden_fixtures_still_reproduce():
         assert e == int(z["expert"])
         assert np.abs(np.array(tr.scores) - z["scores"]).max() < 1e-9
         assert np.abs(out - z["pose"]).max() < 1e-6
+
+
+def test_direct_score_gradient_matches_finite_differences():
+    """Pins the one part of the reference's gradient that IS an exact derivative: d score / d sceneCoordinates at a fixed
+    pose (dScore's direct term, esac_derivative.h:258-306) against central differences of an fp64 restatement of the score
+    (differences through cv2.projectPoints are useless: its float output quantises at ~3e-5 px).
+    The other terms cannot be pinned this way: path I (esac.cpp:373-463) linearises the *norms* of the residuals, which
+    drops a curvature term of the same size as the one it keeps, so the reference's gradient is not the gradient of its own
+    expected loss (measured: finite differences of the refined pose disagree with -(J^T J)^-1 J^T dNdO in sign and size)."""
+    import cv2
+    sc = make_scene(E=1, H=8, W=10, M=6, sub=8, seed=1, outlier_frac=0.0, noise=0.01)
+    H, W = 8, 10
+    K = O.cam_mat(sc.f, sc.ppx, sc.ppy)
+    samp = O.create_sampling(W, H, sc.sub, 0, 0)
+    hyps = O.sample_hypotheses(sc.coords, sc.assign, samp, K, 10000, sc.tau, 5)
+    rng = np.random.default_rng(0)
+    d = rng.normal(size=sc.coords.shape).astype(np.float32)
+    eps = 5e-4
+    cp, cm = (sc.coords + eps * d).astype(np.float32), (sc.coords - eps * d).astype(np.float32)
+
+    def score64(c, rv, tv):
+        R, _ = cv2.Rodrigues(rv)
+        xc = c[0].reshape(3, -1).T.astype(np.float64) @ R.T + tv.ravel()
+        u = xc[:, 0] / xc[:, 2] * sc.f + sc.ppx
+        v = xc[:, 1] / xc[:, 2] * sc.f + sc.ppy
+        px = samp[:, :, 0].reshape(-1).astype(np.float64)
+        py = samp[:, :, 1].reshape(-1).astype(np.float64)
+        err = np.minimum(np.sqrt((u - px) ** 2 + (v - py) ** 2), sc.max_reproj)
+        return (sc.alpha / (H * W)) * np.sum(1 - 1 / (1 + np.exp(-sc.beta * (err - sc.tau))))
+
+    fd, an = [], []
+    pts3, pts2 = O._collect(sc.coords, 0, samp)
+    dcol = d[0].transpose(2, 1, 0).reshape(W * H, 3)
+    for hy in hyps:
+        fd.append((score64(cp, hy.rvec, hy.tvec) - score64(cm, hy.rvec, hy.tvec)) / (2 * eps))
+        err = O.get_repro_errs(sc.coords, hy.rvec, hy.tvec, 0, samp, K, sc.max_reproj)[0]
+        st = 1 / (1 + np.exp(-(sc.beta * (err.astype(np.float64) - sc.tau))))
+        w = -st * (1 - st) * sc.beta * (sc.alpha / (H * W))
+        R, _ = cv2.Rodrigues(hy.rvec)
+        dP = O.d_project_d_obj_batch(pts2, pts3, R, hy.tvec, K, sc.max_reproj) * w.T.reshape(-1)[:, None]
+        an.append(float((dP * dcol).sum()))
+    fd, an = np.array(fd), np.array(an)
+    assert np.corrcoef(fd, an)[0, 1] > 0.995
+    assert np.abs(fd - an).max() < 0.05 * np.abs(fd).max()
