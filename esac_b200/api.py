@@ -62,6 +62,13 @@ def load_library() -> C.CDLL:
     lib.esacb200_backward.argtypes = [vp, vp, vp, i32, i32, i32, vp, i64, i32, vp, f32, f32, f32] + cam + [C.POINTER(f64)]
     lib.esacb200_forward_batch.argtypes = [vp, i32, vp, i32, i32, i32, vp, i64, i32, vp] + cam + [vp]
     lib.esacb200_forward_batch.restype = i32
+    lib.esacb200_backward_batch.argtypes = ([vp, i32, vp, vp, i32, i32, i32, vp, i64, i32, vp, f32, f32, f32, vp, vp] + cam[2:] +
+                                             [vp])
+    lib.esacb200_backward_batch.restype = i32
+    lib.esacb200_assign_hypotheses.argtypes = [vp, i32, i32, i32, vp, i32, i32, C.c_uint64, vp, vp]
+    lib.esacb200_assign_hypotheses.restype = i32
+    lib.esacb200_reproj_loss.argtypes = [vp, i32, vp, vp, i32, i32, vp, vp, vp, f32, f32, f32, i32, f32, f32, f32, vp]
+    lib.esacb200_reproj_loss.restype = i32
     lib.esacb200_backward_sharded.argtypes = ([vp, vp, vp, i32, i32, i32, vp, i64, i32, vp, f32, f32, f32] + cam +
                                                [EXCHANGE_FN, vp, C.POINTER(f64)])
     lib.esacb200_backward_sharded.restype = i32
@@ -416,6 +423,112 @@ def forward_batch(sceneCoordinates, hypAssignment, outPoses, shiftX, shiftY, foc
                                              experts))
     op.finish()
     return [int(e) for e in experts]
+
+
+def backward_batch(sceneCoordinates, outGradients, hypAssignment, gtPoses, wLossRot, wLossTrans, lossCut, shiftX, shiftY,
+                   focalLength, ppointX, ppointY, inlierThreshold, inlierAlpha, inlierBeta, maxReproj, subSampling) -> list:
+    """esac.backward over a batch: sceneCoordinates / outGradients [B,E,3,H,W] float32 (gradients accumulated in place),
+    hypAssignment [B,M] int64, gtPoses [B,4,4] float32 (camera->world), shiftX / shiftY an int or a sequence of B ints
+    (train_esac.py:125 draws one shift per image).  Returns the expected loss of every image; equal, image by image, to B
+    consecutive esac.backward calls on the same context."""
+    _check(sceneCoordinates, "Float", 5, "sceneCoordinates")
+    _check(outGradients, "Float", 5, "outGradients")
+    _check(hypAssignment, "Long", 2, "hypAssignment")
+    _check(gtPoses, "Float", 3, "gtPoses")
+    B, E, C3, H, W = (int(v) for v in sceneCoordinates.shape)
+    if (C3 != 3 or tuple(outGradients.shape) != tuple(sceneCoordinates.shape) or tuple(gtPoses.shape) != (B, 4, 4)
+            or int(hypAssignment.shape[0]) != B):
+        raise RuntimeError("shapes must be [B,E,3,H,W], [B,E,3,H,W], [B,M], [B,4,4]")
+    co = _Arg(sceneCoordinates)
+    og = _Arg(outGradients, writable=True)
+    ha = _Arg(hypAssignment)
+    gt = _Arg(gtPoses)
+    M = int(hypAssignment.shape[1])
+
+    def shifts(v):
+        if isinstance(v, (int, float)):
+            v = [int(v)] * B
+        a = np.ascontiguousarray(np.asarray(v, dtype=np.int32).reshape(-1))
+        if a.shape[0] != B:
+            raise RuntimeError(f"shift must be an int or {B} ints")
+        return a
+
+    sx, sy = shifts(shiftX), shifts(shiftY)
+    ctx = _pick_ctx(co.device, og.device, ha.device, gt.device)
+    losses = np.zeros(B, np.float64)
+    ctx.check(ctx.lib.esacb200_backward_batch(ctx.handle, B, co.ptr, og.ptr, E, H, W, ha.ptr, 1, M, gt.ptr, float(wLossRot),
+                                              float(wLossTrans), float(lossCut), sx.ctypes.data, sy.ctypes.data,
+                                              float(focalLength), float(ppointX), float(ppointY), float(inlierThreshold),
+                                              float(inlierAlpha), float(inlierBeta), float(maxReproj), int(subSampling),
+                                              losses.ctypes.data))
+    og.finish()
+    return [float(v) for v in losses]
+
+
+def assign_hypotheses(gatingProbs, hypotheses: int, seed: int, maxExperts: int = -1, expertSelection: bool = False):
+    """The callers' hypothesis assignment (util.clamp_probs + torch.multinomial(replacement=True) + torch.histc,
+    train_esac.py:130-140, test_esac.py:169-177) for a batch of gating outputs, on the device.  gatingProbs [B,E] float32
+    (CPU, CUDA or numpy; need not be normalised).  Returns (e_hyps int64 [B,M], e_hyps_hist float32 [B,E]) of the same
+    kind as the input.  A pure function of (seed, image, hypothesis); see oracle.esac_oracle.assign_hypotheses."""
+    _check(gatingProbs, "Float", 2, "gatingProbs")
+    B, E = (int(v) for v in gatingProbs.shape)
+    M = int(hypotheses)
+    gp = _Arg(gatingProbs)
+    if _is_torch(gatingProbs):
+        import torch
+        assign = torch.empty((B, M), dtype=torch.int64, device=gatingProbs.device)
+        hist = torch.empty((B, E), dtype=torch.float32, device=gatingProbs.device)
+        ap, hp = assign.data_ptr(), hist.data_ptr()
+    else:
+        assign = np.empty((B, M), np.int64)
+        hist = np.empty((B, E), np.float32)
+        ap, hp = assign.ctypes.data, hist.ctypes.data
+    ctx = _pick_ctx(gp.device)
+    ctx.check(ctx.lib.esacb200_assign_hypotheses(ctx.handle, B, E, M, gp.ptr, int(maxExperts), int(bool(expertSelection)),
+                                                 int(seed) & 0xFFFFFFFFFFFFFFFF, ap, hp))
+    return assign, hist
+
+
+def reproj_loss(prediction, gtPoses, focalLength, padX, padY, cutLoss, subSampling=8, ppointX=None, ppointY=None,
+                outGradients=None, maxReproj=100.0, minDepth=0.1):
+    """The robust reprojection loss of ref_expert.py:103-148 and, when outGradients is given, d loss / d prediction in the
+    same pass (what `robust_loss.backward()` hands to the expert, ref_expert.py:150).  prediction [B,3,H,W] float32 (the
+    reference has B = 1), gtPoses [B,4,4] float32 camera->world, padX / padY an int or B ints (the random shift),
+    outGradients [B,3,H,W] float32 written in place (overwritten) or None.  The principal point defaults to the centre of
+    the sub*W x sub*H image (ref_expert.py:118-119).  Returns the B losses."""
+    _check(prediction, "Float", 4, "prediction")
+    _check(gtPoses, "Float", 3, "gtPoses")
+    B, C3, H, W = (int(v) for v in prediction.shape)
+    if C3 != 3 or tuple(gtPoses.shape) != (B, 4, 4):
+        raise RuntimeError("shapes must be [B,3,H,W] and [B,4,4]")
+    pr = _Arg(prediction)
+    gt = _Arg(gtPoses)
+    og = None
+    if outGradients is not None:
+        _check(outGradients, "Float", 4, "outGradients")
+        if tuple(outGradients.shape) != tuple(prediction.shape):
+            raise RuntimeError("outGradients must have the shape of prediction")
+        og = _Arg(outGradients, writable=True)
+
+    def shifts(v):
+        if isinstance(v, (int, float)):
+            v = [int(v)] * B
+        a = np.ascontiguousarray(np.asarray(v, dtype=np.int32).reshape(-1))
+        if a.shape[0] != B:
+            raise RuntimeError(f"pad must be an int or {B} ints")
+        return a
+
+    sx, sy = shifts(padX), shifts(padY)
+    ppx = float(W * subSampling / 2 if ppointX is None else ppointX)
+    ppy = float(H * subSampling / 2 if ppointY is None else ppointY)
+    ctx = _pick_ctx(pr.device, gt.device, og.device if og else None)
+    losses = np.zeros(B, np.float64)
+    ctx.check(ctx.lib.esacb200_reproj_loss(ctx.handle, B, pr.ptr, og.ptr if og else None, H, W, gt.ptr, sx.ctypes.data,
+                                           sy.ctypes.data, float(focalLength), ppx, ppy, int(subSampling), float(cutLoss),
+                                           float(maxReproj), float(minDepth), losses.ctypes.data))
+    if og:
+        og.finish()
+    return [float(v) for v in losses]
 
 
 

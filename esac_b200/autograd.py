@@ -35,3 +35,29 @@ def esac_loss(scene_coordinates, gating_log_probs, hyp_assignment, gt_pose, *par
     """params: wLossRot, wLossTrans, lossCut, shiftX, shiftY, focalLength, ppointX, ppointY, inlierThreshold,
     inlierAlpha, inlierBeta, maxReproj, subSampling -- the positional tail of esac.backward."""
     return EsacLoss.apply(scene_coordinates, gating_log_probs, hyp_assignment, gt_pose, *params)
+
+
+class ReprojLoss(torch.autograd.Function):
+    """ref_expert.py:103-150 as one autograd node: forward = the robust reprojection loss of a batch of predictions
+    (mean over the batch of the per-image losses; the reference has one image per step), backward = its gradient, both
+    from the single fused kernel behind api.reproj_loss."""
+
+    @staticmethod
+    def forward(ctx, prediction, gt_poses, focal_length, pad_x, pad_y, cut_loss, sub_sampling, ppoint_x, ppoint_y):
+        grads = torch.empty_like(prediction)
+        losses = api.reproj_loss(prediction.detach(), gt_poses, focal_length, pad_x, pad_y, cut_loss, sub_sampling, ppoint_x,
+                                 ppoint_y, outGradients=grads)
+        ctx.save_for_backward(grads)
+        ctx.batch = len(losses)
+        return prediction.new_tensor(sum(losses) / len(losses))
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        (grads,) = ctx.saved_tensors
+        return (grads * (grad_out / ctx.batch),) + (None,) * 8
+
+
+def reproj_loss(prediction, gt_poses, focal_length, pad_x, pad_y, cut_loss, sub_sampling=8, ppoint_x=None, ppoint_y=None):
+    """Drop-in for the loss block of ref_expert.py: `robust_loss = reproj_loss(prediction, gt_pose, f, padX, padY,
+    opt.cutloss)` followed by `robust_loss.backward()`.  prediction [B,3,H,W] (CUDA), gt_poses [B,4,4] camera->world."""
+    return ReprojLoss.apply(prediction, gt_poses, focal_length, pad_x, pad_y, cut_loss, sub_sampling, ppoint_x, ppoint_y)

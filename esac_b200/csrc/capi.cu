@@ -10,6 +10,8 @@
 #include <string.h>
 
 #include <vector>
+#include <thread>
+#include <chrono>
 
 #include "../../include/esac_b200.h"
 #include "../../include/esac_b200_testhooks.h"
@@ -78,6 +80,8 @@ struct esacb200_ctx {
     esacb200_stats st;
     int last_M = 0;
     bool last_backward = false;
+    int batch_workers = 4;
+    std::vector<esacb200_ctx*> workers;  // lazily created contexts of esacb200_backward_batch (own stream + workspace each)
 };
 
 namespace {
@@ -420,6 +424,8 @@ int esacb200_create(int device, esacb200_ctx** out) {
 
 void esacb200_destroy(esacb200_ctx* ctx) {
     if (!ctx) return;
+    for (esacb200_ctx* w : ctx->workers) esacb200_destroy(w);
+    ctx->workers.clear();
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
     DevBuf* bufs[] = {&ctx->coords, &ctx->grads, &ctx->assign64, &ctx->assign32, &ctx->counts, &ctx->offsets, &ctx->perm,
@@ -466,6 +472,7 @@ int esacb200_set_option(esacb200_ctx* ctx, const char* key, double v) {
     else if (!strcmp(key, "hyp_offset")) ctx->hyp_offset = (int)v;  // global index of local hypothesis 0 (sharded runs)
     else if (!strcmp(key, "score_ppt")) ctx->score_ppt_opt = (int)v;   // 0 = automatic, else 2 / 4 / 8 cells per thread
     else if (!strcmp(key, "score_hc")) ctx->score_hc_opt = (int)v;     // 0 = automatic, else hypotheses per chunk (<= 64)
+    else if (!strcmp(key, "batch_workers")) ctx->batch_workers = v < 1 ? 1 : (v > 16 ? 16 : (int)v);  // streams of backward_batch
     else return fail(ctx, ESACB200_ERR_ARG, "unknown option '%s'", key);
     return ESACB200_OK;
 }
@@ -824,6 +831,197 @@ int esacb200_backward_sharded(esacb200_ctx* ctx, const float* coords, float* gra
     if (!exchange) return ctx ? fail(ctx, ESACB200_ERR_ARG, "exchange callback is null") : ESACB200_ERR_ARG;
     return backward_impl(ctx, coords, grads, E, H, W, assign, assign_stride, M, gt_pose, wRot, wTrans, cut, shiftX, shiftY, f, ppx,
                          ppy, tau, alpha, beta, maxReproj, sub, exchange, user, out_loss);
+}
+
+// -------------------------------------------------------------------------------------------------
+// esac_backward over a batch.  Every image is an independent problem ("images in a batch are fully
+// independent"), so the images are dealt round-robin to a few worker contexts, each driven by its own host thread on its
+// own stream: the small kernels of one image fill the gaps the host synchronisations of another leave.
+int esacb200_backward_batch(esacb200_ctx* ctx, int B, const float* coords, float* grads, int E, int H, int W,
+                            const int64_t* assign, int64_t assign_stride, int M, const float* gt_poses, float wRot,
+                            float wTrans, float cut, const int* shiftX, const int* shiftY, float f, float ppx, float ppy,
+                            float tau, float alpha, float beta, float maxReproj, int sub, double* out_losses) {
+    if (!ctx) return ESACB200_ERR_ARG;
+    if (!coords || !grads || !assign || !gt_poses || B <= 0) return fail(ctx, ESACB200_ERR_ARG, "null pointer argument or empty batch");
+    if (ctx->inj_M) return fail(ctx, ESACB200_ERR_ARG, "injected cells are a single-image test hook");
+    if (E <= 0 || H <= 0 || W <= 0 || M <= 0) return fail(ctx, ESACB200_ERR_ARG, "bad sizes E=%d H=%d W=%d M=%d", E, H, W, M);
+    cudaSetDevice(ctx->device);
+    const size_t cstride = (size_t)E * 3 * H * W;
+    const int64_t arow = assign_stride == 0 ? 0 : (int64_t)M * assign_stride;
+    std::vector<float> gt_host;
+    const float* gt = gt_poses;
+    if (is_device_ptr(gt_poses)) {
+        gt_host.resize((size_t)B * 16);
+        CK(cudaMemcpyAsync(gt_host.data(), gt_poses, gt_host.size() * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
+        gt = gt_host.data();
+    }
+    // everything the caller queued on its stream (the experts' outputs) is visible to the workers after this
+    CK(cudaStreamSynchronize(ctx->stream));
+    std::vector<uint64_t> seeds((size_t)B);
+    for (int b = 0; b < B; ++b) seeds[b] = call_seed(ctx);
+    const int nw = ctx->batch_workers < B ? ctx->batch_workers : B;
+    while ((int)ctx->workers.size() < nw) {
+        esacb200_ctx* w = nullptr;
+        int rc = esacb200_create(ctx->device, &w);
+        if (rc) return fail(ctx, rc, "cannot create batch worker context");
+        ctx->workers.push_back(w);
+    }
+    std::vector<int> rcs((size_t)nw, 0), failed_at((size_t)nw, -1);
+    std::vector<esacb200_stats> last((size_t)nw);
+    std::vector<unsigned long long> launches((size_t)nw, 0);
+    auto work = [&](int wi) {
+        esacb200_ctx* w = ctx->workers[wi];
+        cudaSetDevice(ctx->device);
+        w->max_tries = ctx->max_tries;
+        w->max_ref_steps = ctx->max_ref_steps;
+        w->refine_group_opt = ctx->refine_group_opt;
+        w->sample_prefilter = ctx->sample_prefilter;
+        w->hyp_offset = ctx->hyp_offset;
+        w->score_ppt_opt = ctx->score_ppt_opt;
+        w->score_hc_opt = ctx->score_hc_opt;
+        w->fixed_seed = 1;
+        for (int b = wi; b < B; b += nw) {
+            w->seed = seeds[b];
+            double loss = 0;
+            int rc = backward_impl(w, coords + (size_t)b * cstride, grads + (size_t)b * cstride, E, H, W, assign + (size_t)b * arow,
+                                   assign_stride, M, gt + (size_t)b * 16, wRot, wTrans, cut, shiftX ? shiftX[b] : 0,
+                                   shiftY ? shiftY[b] : 0, f, ppx, ppy, tau, alpha, beta, maxReproj, sub, nullptr, nullptr, &loss);
+            if (rc) { rcs[wi] = rc; failed_at[wi] = b; return; }
+            if (out_losses) out_losses[b] = loss;
+            launches[wi] += w->st.kernel_launches;
+        }
+        last[wi] = w->st;
+    };
+    const auto t0 = std::chrono::steady_clock::now();
+    if (nw == 1) {
+        work(0);
+    } else {
+        std::vector<std::thread> th;
+        for (int wi = 0; wi < nw; ++wi) th.emplace_back(work, wi);
+        for (auto& t : th) t.join();
+    }
+    const double wall_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+    for (int wi = 0; wi < nw; ++wi)
+        if (rcs[wi]) return fail(ctx, rcs[wi], "image %d: %s", failed_at[wi], ctx->workers[wi]->err);
+    // statistics of the call: those of the worker that handled the last image, wall time and launches of the whole batch
+    ctx->st = last[(B - 1) % nw];
+    unsigned long long total = 0;
+    for (int wi = 0; wi < nw; ++wi) total += launches[wi];
+    ctx->st.kernel_launches = total;
+    ctx->st.ms_total = (float)wall_ms;
+    ctx->last_M = 0;  // the per-hypothesis buffers live in the workers
+    ctx->last_backward = true;
+    return ESACB200_OK;
+}
+
+// -------------------------------------------------------------------------------------------------
+int esacb200_assign_hypotheses(esacb200_ctx* ctx, int B, int E, int M, const float* weights, int keep_top, int single_expert,
+                               uint64_t seed, int64_t* out_assign, float* out_hist) {
+    if (!ctx) return ESACB200_ERR_ARG;
+    if (!weights || !out_assign) return fail(ctx, ESACB200_ERR_ARG, "null pointer argument");
+    if (B <= 0 || E <= 0 || M <= 0) return fail(ctx, ESACB200_ERR_ARG, "bad sizes B=%d E=%d M=%d", B, E, M);
+    if (E > assign_max_experts()) return fail(ctx, ESACB200_ERR_ARG, "E=%d exceeds the %d experts one CTA holds", E, assign_max_experts());
+    cudaSetDevice(ctx->device);
+    const bool w_host = !is_device_ptr(weights), a_host = !is_device_ptr(out_assign), h_host = out_hist && !is_device_ptr(out_hist);
+    const size_t wb = (size_t)B * E * sizeof(float), ab = (size_t)B * M * sizeof(int64_t);
+    // staging layout in `scratch`: [flags int (16 B)] [weights] [hist] [assign]
+    const size_t off_w = 16, off_h = off_w + ((wb + 15) & ~(size_t)15), off_a = off_h + ((wb + 15) & ~(size_t)15);
+    CK(ctx->scratch.ensure(off_a + ab));
+    char* base = (char*)ctx->scratch.p;
+    const float* d_w = weights;
+    if (w_host) {
+        CK(cudaMemcpyAsync(base + off_w, weights, wb, cudaMemcpyHostToDevice, ctx->stream));
+        d_w = (const float*)(base + off_w);
+    }
+    int64_t* d_a = a_host ? (int64_t*)(base + off_a) : out_assign;
+    float* d_h = !out_hist ? nullptr : (h_host ? (float*)(base + off_h) : out_hist);
+    CK(cudaMemsetAsync(base, 0, 16, ctx->stream));
+    launch_assign(d_w, B, E, M, keep_top, single_expert, seed, d_a, d_h, (int*)base, ctx->stream);
+    CK(cudaGetLastError());
+    if (a_host) CK(cudaMemcpyAsync(out_assign, d_a, ab, cudaMemcpyDeviceToHost, ctx->stream));
+    if (h_host) CK(cudaMemcpyAsync(out_hist, d_h, wb, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaMemcpyAsync(ctx->h_out + 30, base, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    const int flags = *(const int*)(ctx->h_out + 30);
+    if (flags & 1) return fail(ctx, ESACB200_ERR_ARG, "probability tensor contains either inf, nan or element < 0");
+    if (flags & 2) return fail(ctx, ESACB200_ERR_ARG, "invalid multinomial distribution (sum of probabilities <= 0)");
+    return ESACB200_OK;
+}
+
+// -------------------------------------------------------------------------------------------------
+int esacb200_reproj_loss(esacb200_ctx* ctx, int B, const float* coords, float* grads, int H, int W, const float* gt_poses,
+                         const int* shiftX, const int* shiftY, float f, float ppx, float ppy, int sub, float cut,
+                         float maxReproj, float minDepth, double* out_losses) {
+    if (!ctx) return ESACB200_ERR_ARG;
+    if (!coords || !gt_poses || !out_losses) return fail(ctx, ESACB200_ERR_ARG, "null pointer argument");
+    if (B <= 0 || H <= 0 || W <= 0 || sub <= 0) return fail(ctx, ESACB200_ERR_ARG, "bad sizes B=%d H=%d W=%d sub=%d", B, H, W, sub);
+    if ((long long)H * W > (1ll << 30)) return fail(ctx, ESACB200_ERR_ARG, "map %dx%d too large", W, H);
+    cudaSetDevice(ctx->device);
+    begin_call(ctx);
+    const int N = H * W;
+    const size_t cbytes = (size_t)B * 3 * N * sizeof(float);
+    const bool c_host = !is_device_ptr(coords), g_host = grads && !is_device_ptr(grads);
+    const float* d_coords = coords;
+    float* d_grads = grads;
+    if (c_host) {
+        CK(ctx->coords.ensure(cbytes));
+        CK(cudaMemcpyAsync(ctx->coords.p, coords, cbytes, cudaMemcpyHostToDevice, ctx->stream));
+        d_coords = ctx->coords.as<float>();
+    }
+    if (g_host) {
+        CK(ctx->grads.ensure(cbytes));
+        d_grads = ctx->grads.as<float>();
+    }
+    std::vector<float> gt((size_t)B * 16);
+    if (is_device_ptr(gt_poses)) {
+        CK(cudaMemcpyAsync(gt.data(), gt_poses, gt.size() * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
+        CK(cudaStreamSynchronize(ctx->stream));
+    } else {
+        memcpy(gt.data(), gt_poses, gt.size() * sizeof(float));
+    }
+    // world->camera rows: inverse of the affine camera->world matrix (torch's .inverse()[0:3,:], ref_expert.py:127)
+    std::vector<float> img((size_t)B * 16, 0.f);
+    for (int b = 0; b < B; ++b) {
+        const float* T = gt.data() + (size_t)b * 16;
+        double A[9], inv[9];
+        for (int r = 0; r < 3; ++r)
+            for (int c = 0; c < 3; ++c) A[r * 3 + c] = T[r * 4 + c];
+        const double det = A[0] * (A[4] * A[8] - A[5] * A[7]) - A[1] * (A[3] * A[8] - A[5] * A[6]) + A[2] * (A[3] * A[7] - A[4] * A[6]);
+        if (det == 0. || !(det == det)) return fail(ctx, ESACB200_ERR_ARG, "image %d: ground-truth pose is singular", b);
+        inv[0] = (A[4] * A[8] - A[5] * A[7]) / det; inv[1] = (A[2] * A[7] - A[1] * A[8]) / det; inv[2] = (A[1] * A[5] - A[2] * A[4]) / det;
+        inv[3] = (A[5] * A[6] - A[3] * A[8]) / det; inv[4] = (A[0] * A[8] - A[2] * A[6]) / det; inv[5] = (A[2] * A[3] - A[0] * A[5]) / det;
+        inv[6] = (A[3] * A[7] - A[4] * A[6]) / det; inv[7] = (A[1] * A[6] - A[0] * A[7]) / det; inv[8] = (A[0] * A[4] - A[1] * A[3]) / det;
+        float* o = img.data() + (size_t)b * 16;
+        for (int r = 0; r < 3; ++r) {
+            for (int c = 0; c < 3; ++c) o[r * 4 + c] = (float)inv[r * 3 + c];
+            o[r * 4 + 3] = (float)-(inv[r * 3] * T[3] + inv[r * 3 + 1] * T[7] + inv[r * 3 + 2] * T[11]);
+        }
+        o[12] = shiftX ? (float)shiftX[b] : 0.f;
+        o[13] = shiftY ? (float)shiftY[b] : 0.f;
+    }
+    const int bpi = reproj_blocks_per_image(N, B, ctx->sm_count);
+    // scratch layout: [tickets B u32, padded] [img B*16 f32] [losses B f64] [partials B*bpi f64]
+    const size_t off_img = ((size_t)B * 4 + 63) & ~(size_t)63, off_loss = off_img + (size_t)B * 64,
+                 off_part = off_loss + (((size_t)B * 8 + 63) & ~(size_t)63);
+    CK(ctx->scratch.ensure(off_part + (size_t)B * bpi * 8));
+    char* base = (char*)ctx->scratch.p;
+    CK(cudaMemsetAsync(base, 0, off_img, ctx->stream));
+    CK(cudaMemcpyAsync(base + off_img, img.data(), img.size() * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
+    mark(ctx, EV_H2D);
+    mark(ctx, EV_FOLD);  // ms_score = the kernel alone
+    launch_reproj(d_coords, d_grads, (const float*)(base + off_img), B, N, W, (float)sub, f, ppx, ppy, cut, maxReproj, minDepth, bpi,
+                  (double*)(base + off_part), (unsigned*)base, (double*)(base + off_loss), ctx->stream);
+    CK(cudaGetLastError());
+    ctx->st.kernel_launches += 1;
+    mark(ctx, EV_SCORE);
+    if (g_host) CK(cudaMemcpyAsync(grads, d_grads, cbytes, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaMemcpyAsync(out_losses, base + off_loss, (size_t)B * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    mark(ctx, EV_END);
+    CK(cudaStreamSynchronize(ctx->stream));
+    CK(cudaGetLastError());
+    ctx->last_M = 0;
+    finish_stats(ctx);
+    return ESACB200_OK;
 }
 
 int esacb200_copy_last_scores(esacb200_ctx* ctx, double* dst, int M) {

@@ -140,6 +140,19 @@ int refine_max_coresident_blocks(int sm_count);
 void launch_finish_forward(const Pose* poses, const int* winner, const int* assign32, const int* flags, float* out20,
                            cudaStream_t st);
 
+// --- gating.cu ----------------------------------------------------------------------------
+int assign_max_experts();
+void launch_assign(const float* weights, int B, int E, int M, int keep_top, int single, uint64_t seed, int64_t* out_assign,
+                   float* out_hist, int* flags, cudaStream_t stream);
+
+// --- reproj.cu ----------------------------------------------------------------------------
+int reproj_blocks_per_image(int N, int B, int sm_count);
+// img: per image 16 floats = world->camera 3x4 (row major), padX, padY, 2 unused.  partial: B * blocks_per_image doubles,
+// tickets: B zeroed counters (left zeroed), losses: B doubles.  grads may be null (loss only).
+void launch_reproj(const float* coords, float* grads, const float* img, int B, int N, int W, float sub, float f, float cx,
+                   float cy, float cut, float max_err, float min_depth, int blocks_per_image, double* partial,
+                   unsigned* tickets, double* losses, cudaStream_t stream);
+
 // --- bwd.cu -------------------------------------------------------------------------------
 struct BwdArgs {
     const float* coords;

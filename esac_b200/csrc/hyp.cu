@@ -13,7 +13,8 @@
 //                        the 4th point by > 4 tau (>95% on wrong experts); survivors are appended to a global list
 //     exact_kernel       one thread per survivor: the fp64 path (p3p_pose + minimal_set_gate) whose verdict is the
 //                        only one that counts; atomicMin keeps the lowest accepted try per hypothesis
-//     advance_kernel     marks resolved hypotheses, advances the window of the others, rebuilds the work list
+//     (advance)          the last CTA of exact_kernel marks resolved hypotheses, advances the window of the others and
+//                        rebuilds the work list
 //   tail_kernel          CTA per still-unresolved hypothesis: same two phases inside one CTA up to max_tries
 //   emit_kernel          one thread per hypothesis: re-derives the winning (or, when exhausted, the last) try and
 //                        writes pose / cells / try count
@@ -85,7 +86,7 @@ __global__ void interleave_kernel(const float* __restrict__ coords, float4* __re
 __global__ void sample_init_kernel(SampleState st, int M) {
     const int h = blockIdx.x * blockDim.x + threadIdx.x;
     if (h < M) { st.best[h] = kNoKey; st.base[h] = 0; st.ovf[h] = kNoTry; st.list[h] = h; }
-    if (h == 0) { st.counters[0] = M; st.counters[1] = 0; st.counters[2] = 0; st.counters[3] = 128; }  // unresolved, survivors, -, span
+    if (h == 0) { st.counters[0] = M; st.counters[1] = 0; st.counters[2] = 0; st.counters[3] = 128; st.counters[4] = 0; }  // unresolved, survivors, staged, span, ticket
 }
 
 // ---- wave phase 1: fp32 prefilter, one thread per try --------------------------------------------------------
@@ -123,6 +124,8 @@ __global__ void __launch_bounds__(kTryThreads) prefilter_kernel(const __grid_con
     }
 }
 
+__device__ void advance_wave(const SampleState& st, int limit);
+
 // ---- wave phase 2: exact fp64 verdict on the survivors -------------------------------------------------------
 __global__ void __launch_bounds__(128) exact_kernel(const __grid_constant__ SampleArgs a) {
     const int n = min(a.st.counters[1], a.st.cap);
@@ -145,10 +148,20 @@ __global__ void __launch_bounds__(128) exact_kernel(const __grid_constant__ Samp
             atomicMin(&a.st.best[ht.x], ((unsigned long long)(unsigned)ht.y << 32) | slot);
         }
     }
+    // the last CTA to get here has every verdict of the wave in front of it: it does the bookkeeping
+    __shared__ int s_last;
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) s_last = atomicAdd(&a.st.counters[4], 1) == (int)gridDim.x - 1;
+    __syncthreads();
+    if (s_last) {
+        __threadfence();
+        advance_wave(a.st, a.limit);
+    }
 }
 
-// ---- wave phase 3: bookkeeping ------------------------------------------------------------------------------
-__global__ void __launch_bounds__(1024) advance_kernel(SampleState st, int limit) {
+// ---- wave phase 3: bookkeeping (run by the last CTA of exact_kernel to finish) -------------------------------------
+__device__ void advance_wave(const SampleState& st, int limit) {
     __shared__ int s_fill;
     const int span = st.counters[3];
     if (threadIdx.x == 0) s_fill = 0;
@@ -160,9 +173,10 @@ __global__ void __launch_bounds__(1024) advance_kernel(SampleState st, int limit
         const int h = st.list[u];
         const int ovf = st.ovf[h];
         const int end = min(st.base[h] + span, ovf);  // tries below `end` have all been judged
-        const bool resolved = (long long)(st.best[h] >> 32) < (long long)end;
+        const unsigned long long best = __ldcg(&st.best[h]);
+        const bool resolved = (long long)(best >> 32) < (long long)end;
         if (!resolved) {
-            if (st.best[h] != kNoKey) st.best[h] = kNoKey;  // an accept beyond an overflow hole does not count yet
+            if (best != kNoKey) st.best[h] = kNoKey;  // an accept beyond an overflow hole does not count yet
             st.base[h] = end;
             st.ovf[h] = kNoTry;
             if (end < limit) next[atomicAdd(&s_fill, 1)] = h;
@@ -181,6 +195,7 @@ __global__ void __launch_bounds__(1024) advance_kernel(SampleState st, int limit
         st.counters[3] = ((int)next_span + kTryThreads - 1) / kTryThreads * kTryThreads;
         st.counters[0] = nn;
         st.counters[1] = 0;
+        st.counters[4] = 0;  // ticket of the next exact_kernel
     }
 }
 
@@ -257,8 +272,7 @@ int launch_sample(const float* coords, float4* coords4, const int* assign32, con
     const int grid = sm_count * 16;
     for (int r = 0; r < kWaves; ++r) {
         prefilter_kernel<<<grid, kTryThreads, 0, stream>>>(a); ++launches;
-        exact_kernel<<<sm_count * 4, 128, 0, stream>>>(a); ++launches;
-        advance_kernel<<<1, 1024, 0, stream>>>(st, a.limit); ++launches;
+        exact_kernel<<<sm_count * 4, 128, 0, stream>>>(a); ++launches;  // its last CTA also advances the windows
     }
     const int covered = 0;
     if (covered < a.limit) { tail_kernel<<<P.M < sm_count * 4 ? P.M : sm_count * 4, kTryThreads, 0, stream>>>(a); ++launches; }

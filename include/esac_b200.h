@@ -98,6 +98,39 @@ int esacb200_forward_batch(esacb200_ctx* ctx, int B, const float* coords, int E,
                            float ppointX, float ppointY, float inlierThreshold, float inlierAlpha, float inlierBeta,
                            float maxReproj, int subSampling, int* out_experts);
 
+/* esac_backward over B images of one shape (the reference trains with batch_size=1, train_esac.py:96-100, one
+ * esac.backward per image): coords / grads float32 [B,E,3,H,W] (grads accumulated in place, as esac.cpp:490-508),
+ * assign int64 [B,M] (as in esacb200_forward_batch), gt_poses float32 [B,4,4] (camera->world), shiftX / shiftY int [B]
+ * on the host or NULL (= 0: the per-image random shift of train_esac.py:125), out_losses host double [B].
+ * Image b draws the minimal sets that the b-th of B consecutive esacb200_backward calls on this context would draw, so
+ * the batch returns exactly what that loop returns; images are spread over option "batch_workers" (default 4) internal
+ * streams, each with its own workspace and host thread, so their kernels and the per-image host synchronisations overlap. */
+int esacb200_backward_batch(esacb200_ctx* ctx, int B, const float* coords, float* grads, int E, int H, int W,
+                            const int64_t* assign, int64_t assign_stride, int M, const float* gt_poses, float wLossRot,
+                            float wLossTrans, float lossCut, const int* shiftX, const int* shiftY, float focalLength,
+                            float ppointX, float ppointY, float inlierThreshold, float inlierAlpha, float inlierBeta,
+                            float maxReproj, int subSampling, double* out_losses);
+
+/* Hypothesis assignment on the device, the three host steps the reference's callers run before esac.forward/backward:
+ * util.clamp_probs (util.py:38-48; keep_top < 0 = off), torch.multinomial(probs, M, replacement=True)
+ * (train_esac.py:133-137, test_esac.py:169-174; single_expert != 0 = one draw expanded to M, the "expertselection" mode)
+ * and torch.histc over the experts (train_esac.py:140).  weights float32 [B,E] >= 0 (host or device, not necessarily
+ * normalised), out_assign int64 [B,M], out_hist float32 [B,E] or NULL (both host or device).  The draws are a pure
+ * function of (seed, image, hypothesis).  Negative / non-finite weights or an all-zero row are an error, as in torch. */
+int esacb200_assign_hypotheses(esacb200_ctx* ctx, int B, int E, int M, const float* weights, int keep_top,
+                               int single_expert, uint64_t seed, int64_t* out_assign, float* out_hist);
+
+/* Robust reprojection loss of the expert refinement stage and its gradient, one fused pass (ref_expert.py:103-146, where
+ * it is six elementwise torch ops + autograd): coords float32 [B,3,H,W] (one expert's prediction per image; the reference
+ * has B = 1), grads float32 [B,3,H,W] or NULL = d loss_b / d coords (overwritten, not accumulated), gt_poses float32
+ * [B,4,4] camera->world (inverted here, ref_expert.py:127), shiftX / shiftY host int [B] or NULL (padX / padY, :110-111),
+ * target pixel of cell (x,y) = (x*sub + sub/2 - padX, y*sub + sub/2 - padY) with real-valued sub/2 (:84-89),
+ * depth clamped from below at minDepth (0.1, :136), error clamped to [0, maxReproj] (100, :142), square-root loss above
+ * cutLoss (:144-146), mean over the H*W cells (:148).  out_losses host double [B].  fp32 arithmetic like the original. */
+int esacb200_reproj_loss(esacb200_ctx* ctx, int B, const float* coords, float* grads, int H, int W, const float* gt_poses,
+                         const int* shiftX, const int* shiftY, float focalLength, float ppointX, float ppointY,
+                         int subSampling, float cutLoss, float maxReproj, float minDepth, double* out_losses);
+
 /* Soft-inlier scores of given poses (getReproErrs + getHypScores, esac_util.h:235-363) without
  * sampling/selection/refinement: poses6 = host double [M][6] (rvec, tvec); out_scores host double [M]. */
 int esacb200_score_poses(esacb200_ctx* ctx, const float* coords, int E, int H, int W, const int64_t* assign,

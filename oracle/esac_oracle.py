@@ -96,6 +96,57 @@ def draw_minimal_set(seed: int, h: int, t: int, W: int, H: int) -> list[tuple[in
 
 
 # --------------------------------------------------------------------------------------
+# hypothesis assignment of the callers (train_esac.py:130-140, test_esac.py:169-177, util.py:38-48)
+# --------------------------------------------------------------------------------------
+def clamp_probs(probs: np.ndarray, n: int) -> np.ndarray:
+    """util.clamp_probs: all entries but the n largest become zero (n < 0: unchanged).  The reference walks the
+    ascending sort order and zeroes the first len-n indices (util.py:43-48); ties are broken as a stable sort does."""
+    probs = np.array(probs, np.float32, copy=True)
+    if n < 0:
+        return probs
+    order = np.argsort(probs, kind="stable")
+    for i, idx in enumerate(order):
+        if i < probs.shape[0] - n:
+            probs[idx] = 0
+    return probs
+
+
+def assign_hypotheses(weights, M: int, seed: int, keep_top: int = -1, single: bool = False):
+    """e_hyps, e_hyps_hist for a batch of gating outputs [B, E]: clamp_probs, then M draws with replacement from the
+    categorical distribution weights/sum(weights) (torch.multinomial semantics: any non-negative weights), then the
+    histogram over experts (torch.histc with one bin per expert).  Draw h of image b inverts the fp64 running sum at
+    u = uniform53(try_state(seed, b, h)) * total; `single` repeats draw 0 (expertselection, train_esac.py:133-135)."""
+    weights = np.asarray(weights, np.float32)
+    B, E = weights.shape
+    assign = np.zeros((B, M), np.int64)
+    hist = np.zeros((B, E), np.float32)
+    for b in range(B):
+        w = clamp_probs(weights[b], keep_top)
+        if not np.all(np.isfinite(w)) or np.any(w < 0):
+            raise RuntimeError("probability tensor contains either inf, nan or element < 0")
+        cdf = np.zeros(E, np.float64)
+        acc = 0.0
+        last_pos = -1
+        for e in range(E):
+            if w[e] > 0:
+                acc += float(w[e])
+                last_pos = e
+            cdf[e] = acc
+        if last_pos < 0:
+            raise RuntimeError("invalid multinomial distribution (sum of probabilities <= 0)")
+        total = cdf[E - 1]
+        for h in range(M):
+            r = try_state(seed, b, 0 if single else h)
+            u = float(r >> 11) * 2.0 ** -53 * total
+            e = int(np.searchsorted(cdf, u, side="right"))  # first e with cdf[e] > u
+            if e >= E:
+                e = last_pos
+            assign[b, h] = e
+            hist[b, e] += 1
+    return assign, hist
+
+
+# --------------------------------------------------------------------------------------
 # small helpers
 # --------------------------------------------------------------------------------------
 def cam_mat(f: float, ppx: float, ppy: float) -> np.ndarray:

@@ -140,3 +140,72 @@ def test_direct_score_gradient_matches_finite_differences():
     fd, an = np.array(fd), np.array(an)
     assert np.corrcoef(fd, an)[0, 1] > 0.995
     assert np.abs(fd - an).max() < 0.05 * np.abs(fd).max()
+
+
+def test_assign_hypotheses_follows_the_callers_semantics():
+    """clamp_probs / multinomial(replacement) / histc as train_esac.py:130-140 runs them, checked against torch."""
+    import torch
+    rng = np.random.default_rng(5)
+    w = rng.random((3, 9)).astype(np.float32)
+    w[0, 4] = 0.0
+    # util.clamp_probs restated with torch.sort exactly as the caller does (util.py:43-48)
+    for n in (-1, 0, 2, 9, 20):
+        t = torch.from_numpy(w[1].copy())
+        if n >= 0:
+            s_prob, s_indx = t.sort(dim=0, stable=True)
+            for i, idx in enumerate(s_indx):
+                if i < s_prob.size(0) - n:
+                    t[idx] = 0
+        assert np.array_equal(O.clamp_probs(w[1], n), t.numpy())
+    a, h = O.assign_hypotheses(w, 4000, seed=11)
+    assert a.shape == (3, 4000) and a.dtype == np.int64
+    for b in range(3):
+        ref_hist = torch.histc(torch.from_numpy(a[b]).float(), bins=9, min=0, max=8).numpy()
+        assert np.array_equal(h[b], ref_hist)
+        p = w[b] / w[b].sum()
+        assert np.abs(h[b] / 4000 - p).max() < 0.03          # ~4 sigma of a binomial proportion
+    assert h[0, 4] == 0                                       # zero weight is never drawn
+    a2, h2 = O.assign_hypotheses(w, 50, seed=11, keep_top=2)
+    for b in range(3):
+        top2 = set(np.argsort(w[b], kind="stable")[-2:].tolist())
+        assert set(np.unique(a2[b]).tolist()) <= top2
+    a3, h3 = O.assign_hypotheses(w, 16, seed=11, single=True)
+    assert all(len(np.unique(a3[b])) == 1 for b in range(3)) and np.all(h3.sum(axis=1) == 16)
+    assert np.array_equal(a3[:, 0], a[:, 0])                  # the single draw is draw 0 of the stream
+    with pytest.raises(RuntimeError):
+        O.assign_hypotheses(np.zeros((1, 4), np.float32), 4, seed=1)
+    with pytest.raises(RuntimeError):
+        O.assign_hypotheses(np.array([[0.5, -0.1]], np.float32), 4, seed=1)
+
+
+def test_reproj_loss_oracle_gradient_matches_closed_form():
+    """The torch restatement of ref_expert.py:103-148 (autograd) against an independent numpy closed form in float64."""
+    import torch
+    from oracle.reproj_loss_oracle import reproj_loss_and_grad
+    sc = make_scene(E=1, H=12, W=15, M=8, sub=8, seed=21, outlier_frac=0.3)
+    f, padx, pady, cut = 525.0, 3, -2, 10.0
+    X = sc.coords[0].astype(np.float64)
+    X[:, 0, 0] = [0.0, 0.0, -50.0]                       # a point behind the camera: depth clamp branch
+    loss, g = reproj_loss_and_grad(torch.from_numpy(X), torch.from_numpy(sc.gt_pose.astype(np.float64)), f, padx, pady, cut,
+                                   dtype=torch.float64)
+    Tinv = np.linalg.inv(sc.gt_pose.astype(np.float64))[:3]
+    H, W = X.shape[1:]
+    cx, cy = W * 8 / 2, H * 8 / 2
+    total = 0.0
+    G = np.zeros_like(X)
+    for y in range(H):
+        for x in range(W):
+            c = Tinv[:, :3] @ X[:, y, x] + Tinv[:, 3]
+            nu, nv = f * c[0] + cx * c[2], f * c[1] + cy * c[2]
+            open_ = c[2] >= 0.1
+            z = c[2] if open_ else 0.1
+            du, dv = nu / z - (x * 8 + 4.0 - padx), nv / z - (y * 8 + 4.0 - pady)
+            err = np.hypot(du, dv)
+            e = min(err, 100.0)
+            total += e if e <= cut else np.sqrt(cut * e)
+            gl = 0.0 if err > 100.0 else (1.0 if e <= cut else 0.5 * cut / np.sqrt(cut * e))
+            gu, gv = gl * du / err, gl * dv / err
+            gc = np.array([gu * f / z, gv * f / z, (gu * cx + gv * cy) / z - ((gu * nu + gv * nv) / z ** 2 if open_ else 0.0)])
+            G[:, y, x] = Tinv[:, :3].T @ gc / (H * W)
+    assert abs(loss - total / (H * W)) < 1e-12 * max(1.0, abs(loss))
+    assert np.abs(g.numpy() - G).max() < 1e-12 * max(1.0, np.abs(G).max())
