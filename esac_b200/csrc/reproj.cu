@@ -22,40 +22,62 @@ constexpr int kCellsPerThread = 4;
 
 struct CellOut { float gx, gy, gz, loss; };
 
-// Arithmetic in fp32 like the torch ops it replaces.  m = rows of the 3x4 world->camera matrix.
+__device__ __forceinline__ float rcp_fast(float x) {   // MUFU.RCP, <= 1 ulp
+    float r;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+}
+__device__ __forceinline__ float rsqrt_fast(float x) { // MUFU.RSQ, <= 2 ulp
+    float r;
+    asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+}
+
+// One cell, fp32 like the torch ops it replaces, arranged so that the kernel stays under the HBM roofline's instruction
+// budget (~70 issue slots per cell, 3 MUFU) and loses no accuracy against the original op sequence:
+//  * the pixel offset is formed as (nu - tx*zz) / zz with one FMA, so the division only ever scales a small number (the
+//    original rounds u = nu/zz at |u| ~ 1e3 px before subtracting);
+//  * where the depth clamp is open, d/dzc collapses to -(gxc*xc + gyc*yc)/zz, free of the cx/zz - u/zz cancellation.
+// m = rows of the 3x4 world->camera matrix.
 __device__ __forceinline__ CellOut reproj_cell(float X, float Y, float Z, const float* __restrict__ m, float f, float cx,
                                                float cy, float tx, float ty, float cut, float max_err, float min_depth,
                                                float inv_n) {
     const float xc = fmaf(m[0], X, fmaf(m[1], Y, fmaf(m[2], Z, m[3])));
     const float yc = fmaf(m[4], X, fmaf(m[5], Y, fmaf(m[6], Z, m[7])));
     const float zc = fmaf(m[8], X, fmaf(m[9], Y, fmaf(m[10], Z, m[11])));
-    const float nu = fmaf(f, xc, cx * zc);
+    const float nu = fmaf(f, xc, cx * zc);         // numerator keeps the unclamped depth (ref_expert.py:135-137)
     const float nv = fmaf(f, yc, cy * zc);
-    const bool open = zc >= min_depth;            // clamp_ passes the gradient where it did not clamp
+    const bool open = zc >= min_depth;             // clamp_ passes the gradient where it did not clamp
     const float zz = open ? zc : min_depth;
-    const float iz = 1.f / zz;
-    const float u = nu * iz, v = nv * iz;
-    const float du = u - tx, dv = v - ty;
-    const float err = sqrtf(du * du + dv * dv);
-    CellOut o;
-    const float e = fminf(err, max_err);          // err >= 0 always
+    const float iz = rcp_fast(zz);
+    const float du = fmaf(-tx, zz, nu) * iz;
+    const float dv = fmaf(-ty, zz, nv) * iz;
+    const float s2 = fmaf(du, du, dv * dv);
+    const float r = s2 > 0.f ? rsqrt_fast(s2) : 0.f;   // 1/err; norm backward is defined as 0 at the origin
+    const float err = s2 * r;
+    const float e = fminf(err, max_err);
+    const float t = cut * e;
+    const float rt = t > 0.f ? rsqrt_fast(t) : 0.f;
     const bool l1 = e <= cut;
-    o.loss = l1 ? e : sqrtf(cut * e);
+    CellOut o;
+    o.loss = l1 ? e : t * rt;                       // sqrt(cut * e)
     // d loss / d err; the clamp's gradient is 1 on [0, max_err] (bounds included) and 0 outside
-    float g = (err <= max_err) ? (l1 ? 1.f : 0.5f * cut / sqrtf(cut * e)) : 0.f;
-    g *= inv_n;
-    // norm backward: x / ||x||, defined as 0 at the origin
-    const float in = err > 0.f ? 1.f / err : 0.f;
-    const float gu = g * du * in, gv = g * dv * in;
-    // u = nu / zz:  du/dxc = f/zz, du/dzc = cx/zz - [open] nu/zz^2   (same for v)
-    const float gxc = gu * f * iz;
-    const float gyc = gv * f * iz;
-    float gzc = (gu * cx + gv * cy) * iz;
-    if (open) gzc -= (gu * nu + gv * nv) * iz * iz;
+    float g = l1 ? 1.f : 0.5f * cut * rt;
+    g = err <= max_err ? g * inv_n : 0.f;
+    const float gr = g * r;
+    const float fiz = f * iz;
+    const float gxc = gr * du * fiz;
+    const float gyc = gr * dv * fiz;
+    const float gz_open = -(gxc * xc + gyc * yc) * iz;
+    const float gz_shut = gr * (du * cx + dv * cy) * iz;
+    const float gzc = open ? gz_open : gz_shut;
     o.gx = fmaf(m[0], gxc, fmaf(m[4], gyc, m[8] * gzc));
     o.gy = fmaf(m[1], gxc, fmaf(m[5], gyc, m[9] * gzc));
     o.gz = fmaf(m[2], gxc, fmaf(m[6], gyc, m[10] * gzc));
-    if (!(err == err)) o.loss = 0.f;              // NaN: in neither branch of the masked sums (its gradient stays NaN, as in torch)
+    if (!(s2 == s2)) {                              // NaN input: in neither branch of the masked sums; gradient NaN as in torch
+        o.loss = 0.f;
+        o.gx = o.gy = o.gz = s2;
+    }
     return o;
 }
 
@@ -104,15 +126,17 @@ __global__ void __launch_bounds__(kThreads) reproj_kernel(const float* __restric
         }
         int y = p0 / W, x = p0 - y * W;
         float ox[4], oy[4], oz[4];
+        float four = 0.f;   // 4 losses <= 100 each: exact enough in fp32; the long sums run in fp64
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
             const float tx = fmaf((float)x, sub, half) - padX;
             const float ty = fmaf((float)y, sub, half) - padY;
             const CellOut o = reproj_cell(X[i], Y[i], Z[i], m, f, cx, cy, tx, ty, cut, max_err, min_depth, inv_n);
-            if (i < n) acc += (double)o.loss;
+            if (i < n) four += o.loss;
             ox[i] = o.gx; oy[i] = o.gy; oz[i] = o.gz;
             if (++x == W) { x = 0; ++y; }
         }
+        acc += (double)four;
         if (gx) {
             if (VEC) {
                 __stcs(reinterpret_cast<float4*>(gx + p0), make_float4(ox[0], ox[1], ox[2], ox[3]));
@@ -127,37 +151,47 @@ __global__ void __launch_bounds__(kThreads) reproj_kernel(const float* __restric
             }
         }
     }
-    // block sum in a fixed order, then the last block of the image adds the partials in block order
+    // block sum in a fixed order, then the last block of the image adds the partials, again in a fixed order
+    auto block_sum = [&](double v) -> double {  // result valid in thread 0
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
-    if ((threadIdx.x & 31) == 0) warp_sum[threadIdx.x >> 5] = acc;
-    __syncthreads();
-    if (threadIdx.x == 0) {
+        for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+        __syncthreads();
+        if ((threadIdx.x & 31) == 0) warp_sum[threadIdx.x >> 5] = v;
+        __syncthreads();
         double s = 0.;
-        for (int w = 0; w < kThreads / 32; ++w) s += warp_sum[w];
-        partial[(size_t)b * gridDim.x + blockIdx.x] = s;
+        if (threadIdx.x == 0)
+            for (int w = 0; w < kThreads / 32; ++w) s += warp_sum[w];
+        return s;
+    };
+    const double mine = block_sum(acc);
+    if (threadIdx.x == 0) {
+        partial[(size_t)b * gridDim.x + blockIdx.x] = mine;
         __threadfence();
         last = atomicAdd(&tickets[b], 1u) == gridDim.x - 1;
     }
     __syncthreads();
-    if (last && threadIdx.x == 0) {
+    if (last) {
         __threadfence();
-        double s = 0.;
-        for (unsigned k = 0; k < gridDim.x; ++k) s += __ldcg(&partial[(size_t)b * gridDim.x + k]);
-        losses[b] = s / (double)N;
-        tickets[b] = 0;  // ready for the next launch
+        double v = 0.;
+        for (unsigned k = threadIdx.x; k < gridDim.x; k += kThreads) v += __ldcg(&partial[(size_t)b * gridDim.x + k]);
+        const double s = block_sum(v);
+        if (threadIdx.x == 0) {
+            losses[b] = s / (double)N;
+            tickets[b] = 0;  // ready for the next launch
+        }
     }
 }
 
 }  // namespace
 
 int reproj_blocks_per_image(int N, int B, int sm_count) {
+    // Many short CTAs (each a few KB of traffic) rather than one resident wave: the hardware scheduler then keeps every SM
+    // streaming to the end, where a persistent grid of sm_count * k CTAs would finish with a ragged tail.  Two passes per
+    // CTA at most, so the count stays a pure function of N (the fixed summation order depends on it).
+    (void)B; (void)sm_count;
     const int per_block = kThreads * kCellsPerThread;
-    int need = (N + per_block - 1) / per_block;
-    // enough CTAs in flight to cover the HBM latency (8 resident CTAs per SM), never more than the work
-    int want = (sm_count * 8 + B - 1) / B;
-    if (want < 1) want = 1;
-    return need < want ? need : want;
+    const int need = (N + per_block - 1) / per_block;
+    return need <= 1024 ? need : (need + 1) / 2;
 }
 
 void launch_reproj(const float* coords, float* grads, const float* img, int B, int N, int W, float sub, float f, float cx,

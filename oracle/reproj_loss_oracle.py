@@ -16,10 +16,11 @@ from __future__ import annotations
 import torch
 
 
-def reproj_loss(prediction: torch.Tensor, gt_pose: torch.Tensor, focallength: float, pad_x: float, pad_y: float,
-                cutloss: float, subsample: int = 8, image_w: float | None = None, image_h: float | None = None,
-                dtype=torch.float32) -> torch.Tensor:
-    """prediction [1 or none,3,h,w] scene coordinates (requires_grad allowed), gt_pose [4,4] camera->world.
+def reproj_errors(prediction: torch.Tensor, gt_pose: torch.Tensor, focallength: float, pad_x: float, pad_y: float,
+                  subsample: int = 8, image_w: float | None = None, image_h: float | None = None,
+                  dtype=torch.float32) -> torch.Tensor:
+    """Per-cell reprojection error clamped to [0, 100] px, flat [h*w] (ref_expert.py:103-142).
+    prediction [1 or none,3,h,w] scene coordinates (requires_grad allowed), gt_pose [4,4] camera->world.
     image_w/h: size of the (padded) input image; default sub*w, sub*h -> principal point at the map centre
     (ref_expert.py:118-119)."""
     if prediction.dim() == 3:
@@ -48,7 +49,14 @@ def reproj_loss(prediction: torch.Tensor, gt_pose: torch.Tensor, focallength: fl
     px = px[0:2] / px[2]                                 # :137
     px = px - grid                                       # :140
     px = px.norm(2, 0)                                   # :141
-    px = px.clamp(0, 100)                                # :142
+    return px.clamp(0, 100)                              # :142
+
+
+def reproj_loss(prediction: torch.Tensor, gt_pose: torch.Tensor, focallength: float, pad_x: float, pad_y: float,
+                cutloss: float, subsample: int = 8, image_w: float | None = None, image_h: float | None = None,
+                dtype=torch.float32) -> torch.Tensor:
+    """The robust loss of ref_expert.py:144-148 over reproj_errors()."""
+    px = reproj_errors(prediction, gt_pose, focallength, pad_x, pad_y, subsample, image_w, image_h, dtype)
     loss_l1 = px[px <= cutloss]                          # :144
     loss_sqrt = px[px > cutloss]                         # :145
     loss_sqrt = torch.sqrt(cutloss * loss_sqrt)          # :146
