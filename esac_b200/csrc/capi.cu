@@ -80,7 +80,7 @@ struct esacb200_ctx {
     esacb200_stats st;
     int last_M = 0;
     bool last_backward = false;
-    int batch_workers = 4;
+    int batch_workers = 8;
     std::vector<esacb200_ctx*> workers;  // lazily created contexts of esacb200_backward_batch (own stream + workspace each)
 };
 

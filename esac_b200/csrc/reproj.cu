@@ -21,6 +21,9 @@ constexpr int kThreads = 256;
 constexpr int kCellsPerThread = 4;
 
 struct CellOut { float gx, gy, gz, loss; };
+struct PairOut { float2 gx, gy, gz, loss; };
+
+constexpr float kTiny = 1e-30f;
 
 __device__ __forceinline__ float rcp_fast(float x) {   // MUFU.RCP, <= 1 ulp
     float r;
@@ -53,11 +56,11 @@ __device__ __forceinline__ CellOut reproj_cell(float X, float Y, float Z, const 
     const float du = fmaf(-tx, zz, nu) * iz;
     const float dv = fmaf(-ty, zz, nv) * iz;
     const float s2 = fmaf(du, du, dv * dv);
-    const float r = s2 > 0.f ? rsqrt_fast(s2) : 0.f;   // 1/err; norm backward is defined as 0 at the origin
+    const float r = rsqrt_fast(fmaxf(s2, kTiny));   // 1/err; at the origin err = s2*r = 0 and the gradient gr*du = 0 (norm backward)
     const float err = s2 * r;
     const float e = fminf(err, max_err);
     const float t = cut * e;
-    const float rt = t > 0.f ? rsqrt_fast(t) : 0.f;
+    const float rt = rsqrt_fast(fmaxf(t, kTiny));
     const bool l1 = e <= cut;
     CellOut o;
     o.loss = l1 ? e : t * rt;                       // sqrt(cut * e)
@@ -81,9 +84,61 @@ __device__ __forceinline__ CellOut reproj_cell(float X, float Y, float Z, const 
     return o;
 }
 
+// Two cells at once on the packed f32x2 pipe (FFMA2 / FMUL2: one issue slot, two IEEE fp32 results -- bitwise what
+// reproj_cell computes for each).  Halves the FMA-pipe instruction count, which is what keeps this kernel from being
+// issue-bound below the HBM roofline.
+struct PairConst {
+    float2 m[12];            // world->camera entries, broadcast
+    float2 f, cx, cy, cut, half_cut, inv_n;
+    float max_err, min_depth, cut_s;
+};
+
+__device__ __forceinline__ float2 bc(float v) { return make_float2(v, v); }
+__device__ __forceinline__ float2 neg2(float2 v) { return make_float2(-v.x, -v.y); }
+
+__device__ __forceinline__ PairOut reproj_pair(float2 X, float2 Y, float2 Z, const PairConst& k, float2 tx, float2 ty) {
+    const float2 xc = __ffma2_rn(k.m[0], X, __ffma2_rn(k.m[1], Y, __ffma2_rn(k.m[2], Z, k.m[3])));
+    const float2 yc = __ffma2_rn(k.m[4], X, __ffma2_rn(k.m[5], Y, __ffma2_rn(k.m[6], Z, k.m[7])));
+    const float2 zc = __ffma2_rn(k.m[8], X, __ffma2_rn(k.m[9], Y, __ffma2_rn(k.m[10], Z, k.m[11])));
+    const float2 nu = __ffma2_rn(k.f, xc, __fmul2_rn(k.cx, zc));
+    const float2 nv = __ffma2_rn(k.f, yc, __fmul2_rn(k.cy, zc));
+    const bool open0 = zc.x >= k.min_depth, open1 = zc.y >= k.min_depth;
+    const float2 zz = make_float2(open0 ? zc.x : k.min_depth, open1 ? zc.y : k.min_depth);
+    const float2 iz = make_float2(rcp_fast(zz.x), rcp_fast(zz.y));
+    const float2 du = __fmul2_rn(__ffma2_rn(neg2(tx), zz, nu), iz);
+    const float2 dv = __fmul2_rn(__ffma2_rn(neg2(ty), zz, nv), iz);
+    const float2 s2 = __ffma2_rn(du, du, __fmul2_rn(dv, dv));
+    const float2 r = make_float2(rsqrt_fast(fmaxf(s2.x, kTiny)), rsqrt_fast(fmaxf(s2.y, kTiny)));
+    const float2 err = __fmul2_rn(s2, r);
+    const float2 e = make_float2(fminf(err.x, k.max_err), fminf(err.y, k.max_err));
+    const float2 t = __fmul2_rn(k.cut, e);
+    const float2 rt = make_float2(rsqrt_fast(fmaxf(t.x, kTiny)), rsqrt_fast(fmaxf(t.y, kTiny)));
+    const float2 sq = __fmul2_rn(t, rt);                  // sqrt(cut * e)
+    const float2 gs = __fmul2_rn(k.half_cut, rt);         // its derivative
+    const bool l0 = e.x <= k.cut_s, l1 = e.y <= k.cut_s;
+    PairOut o;
+    o.loss = make_float2(l0 ? e.x : sq.x, l1 ? e.y : sq.y);
+    float2 g = make_float2(l0 ? 1.f : gs.x, l1 ? 1.f : gs.y);
+    g = __fmul2_rn(g, k.inv_n);
+    g = make_float2(err.x <= k.max_err ? g.x : 0.f, err.y <= k.max_err ? g.y : 0.f);
+    const float2 gr = __fmul2_rn(g, r);
+    const float2 fiz = __fmul2_rn(k.f, iz);
+    const float2 gxc = __fmul2_rn(__fmul2_rn(gr, du), fiz);
+    const float2 gyc = __fmul2_rn(__fmul2_rn(gr, dv), fiz);
+    const float2 go = __fmul2_rn(neg2(__ffma2_rn(gxc, xc, __fmul2_rn(gyc, yc))), iz);
+    const float2 gsh = __fmul2_rn(__fmul2_rn(gr, __ffma2_rn(du, k.cx, __fmul2_rn(dv, k.cy))), iz);
+    const float2 gzc = make_float2(open0 ? go.x : gsh.x, open1 ? go.y : gsh.y);
+    o.gx = __ffma2_rn(k.m[0], gxc, __ffma2_rn(k.m[4], gyc, __fmul2_rn(k.m[8], gzc)));
+    o.gy = __ffma2_rn(k.m[1], gxc, __ffma2_rn(k.m[5], gyc, __fmul2_rn(k.m[9], gzc)));
+    o.gz = __ffma2_rn(k.m[2], gxc, __ffma2_rn(k.m[6], gyc, __fmul2_rn(k.m[10], gzc)));
+    if (!(s2.x == s2.x)) { o.loss.x = 0.f; o.gx.x = o.gy.x = o.gz.x = s2.x; }   // NaN input (see reproj_cell)
+    if (!(s2.y == s2.y)) { o.loss.y = 0.f; o.gx.y = o.gy.y = o.gz.y = s2.y; }
+    return o;
+}
+
 // grid = (blocks_per_image, B).  img[b] = 12 matrix entries, padX, padY, 2 unused.
 template <bool VEC>
-__global__ void __launch_bounds__(kThreads) reproj_kernel(const float* __restrict__ coords, float* __restrict__ grads,
+__global__ void __launch_bounds__(kThreads, 5) reproj_kernel(const float* __restrict__ coords, float* __restrict__ grads,
                                                           const float* __restrict__ img, int N, int W, float sub, float f,
                                                           float cx, float cy, float cut, float max_err, float min_depth,
                                                           double* __restrict__ partial, unsigned* __restrict__ tickets,
@@ -101,6 +156,13 @@ __global__ void __launch_bounds__(kThreads) reproj_kernel(const float* __restric
     const float inv_n = 1.f / (float)N;
     const float half = sub * 0.5f;
     const float padX = m[12], padY = m[13];
+    PairConst kc;
+    if (VEC) {
+#pragma unroll
+        for (int i = 0; i < 12; ++i) kc.m[i] = bc(m[i]);
+        kc.f = bc(f); kc.cx = bc(cx); kc.cy = bc(cy); kc.cut = bc(cut); kc.half_cut = bc(0.5f * cut); kc.inv_n = bc(inv_n);
+        kc.max_err = max_err; kc.min_depth = min_depth; kc.cut_s = cut;
+    }
     double acc = 0.;
     const int per_block = kThreads * kCellsPerThread;
     for (int base = blockIdx.x * per_block; base < N; base += gridDim.x * per_block) {
@@ -127,14 +189,37 @@ __global__ void __launch_bounds__(kThreads) reproj_kernel(const float* __restric
         int y = p0 / W, x = p0 - y * W;
         float ox[4], oy[4], oz[4];
         float four = 0.f;   // 4 losses <= 100 each: exact enough in fp32; the long sums run in fp64
+        if (VEC) {
+            // target pixels of the 4 cells; a row change inside the group moves the later cells to the next row (W >= 4)
+            const float xf = (float)x, yf = (float)y;
+            float txs[4], tys[4];
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
-            const float tx = fmaf((float)x, sub, half) - padX;
-            const float ty = fmaf((float)y, sub, half) - padY;
-            const CellOut o = reproj_cell(X[i], Y[i], Z[i], m, f, cx, cy, tx, ty, cut, max_err, min_depth, inv_n);
-            if (i < n) four += o.loss;
-            ox[i] = o.gx; oy[i] = o.gy; oz[i] = o.gz;
-            if (++x == W) { x = 0; ++y; }
+            for (int i = 0; i < 4; ++i) {
+                const bool wrap = x + i >= W;
+                const float xi = xf + (float)i - (wrap ? (float)W : 0.f);
+                const float yi = yf + (wrap ? 1.f : 0.f);
+                txs[i] = fmaf(xi, sub, half) - padX;
+                tys[i] = fmaf(yi, sub, half) - padY;
+            }
+#pragma unroll
+            for (int i = 0; i < 4; i += 2) {
+                const PairOut o = reproj_pair(make_float2(X[i], X[i + 1]), make_float2(Y[i], Y[i + 1]), make_float2(Z[i], Z[i + 1]),
+                                              kc, make_float2(txs[i], txs[i + 1]), make_float2(tys[i], tys[i + 1]));
+                four += o.loss.x + o.loss.y;
+                ox[i] = o.gx.x; ox[i + 1] = o.gx.y;
+                oy[i] = o.gy.x; oy[i + 1] = o.gy.y;
+                oz[i] = o.gz.x; oz[i + 1] = o.gz.y;
+            }
+        } else {
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const float tx = fmaf((float)x, sub, half) - padX;
+                const float ty = fmaf((float)y, sub, half) - padY;
+                const CellOut o = reproj_cell(X[i], Y[i], Z[i], m, f, cx, cy, tx, ty, cut, max_err, min_depth, inv_n);
+                if (i < n) four += o.loss;
+                ox[i] = o.gx; oy[i] = o.gy; oz[i] = o.gz;
+                if (++x == W) { x = 0; ++y; }
+            }
         }
         acc += (double)four;
         if (gx) {
@@ -198,7 +283,7 @@ void launch_reproj(const float* coords, float* grads, const float* img, int B, i
                    float cy, float cut, float max_err, float min_depth, int blocks_per_image, double* partial,
                    unsigned* tickets, double* losses, cudaStream_t stream) {
     const dim3 grid(blocks_per_image, B);
-    const bool vec = (N % 4 == 0) && ((uintptr_t)coords % 16 == 0) && (!grads || (uintptr_t)grads % 16 == 0);
+    const bool vec = (N % 4 == 0) && W >= 4 && ((uintptr_t)coords % 16 == 0) && (!grads || (uintptr_t)grads % 16 == 0);
     if (vec)
         reproj_kernel<true><<<grid, kThreads, 0, stream>>>(coords, grads, img, N, W, sub, f, cx, cy, cut, max_err, min_depth,
                                                            partial, tickets, losses);

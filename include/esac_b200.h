@@ -103,7 +103,7 @@ int esacb200_forward_batch(esacb200_ctx* ctx, int B, const float* coords, int E,
  * assign int64 [B,M] (as in esacb200_forward_batch), gt_poses float32 [B,4,4] (camera->world), shiftX / shiftY int [B]
  * on the host or NULL (= 0: the per-image random shift of train_esac.py:125), out_losses host double [B].
  * Image b draws the minimal sets that the b-th of B consecutive esacb200_backward calls on this context would draw, so
- * the batch returns exactly what that loop returns; images are spread over option "batch_workers" (default 4) internal
+ * the batch returns exactly what that loop returns; images are spread over option "batch_workers" (default 8) internal
  * streams, each with its own workspace and host thread, so their kernels and the per-image host synchronisations overlap. */
 int esacb200_backward_batch(esacb200_ctx* ctx, int B, const float* coords, float* grads, int E, int H, int W,
                             const int64_t* assign, int64_t assign_stride, int M, const float* gt_poses, float wLossRot,
