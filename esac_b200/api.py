@@ -62,6 +62,8 @@ def load_library() -> C.CDLL:
     lib.esacb200_backward.argtypes = [vp, vp, vp, i32, i32, i32, vp, i64, i32, vp, f32, f32, f32] + cam + [C.POINTER(f64)]
     lib.esacb200_forward_batch.argtypes = [vp, i32, vp, i32, i32, i32, vp, i64, i32, vp] + cam + [vp]
     lib.esacb200_forward_batch.restype = i32
+    lib.esacb200_forward_pack.argtypes = [vp, vp, i32, i32, i32, vp, i64, i32] + cam + [i32, vp]
+    lib.esacb200_forward_pack.restype = i32
     lib.esacb200_backward_batch.argtypes = ([vp, i32, vp, vp, i32, i32, i32, vp, i64, i32, vp, f32, f32, f32, vp, vp] + cam[2:] +
                                              [vp])
     lib.esacb200_backward_batch.restype = i32
@@ -529,6 +531,26 @@ def reproj_loss(prediction, gtPoses, focalLength, padX, padY, cutLoss, subSampli
     if og:
         og.finish()
     return [float(v) for v in losses]
+
+
+def forward_pack(sceneCoordinates, hypAssignment, params, expert_offset: int, pack_out):
+    """The local half of a sharded forward, enqueued on the current CUDA stream without a host synchronisation
+    (esacb200_forward_pack).  sceneCoordinates [E,3,H,W] / hypAssignment [M] are CUDA tensors, params the positional tail of
+    esac.forward (shiftX .. subSampling), pack_out a CUDA float64 tensor of M + 18 elements (see include/esac_b200.h)."""
+    _check(sceneCoordinates, "Float", 4, "sceneCoordinates")
+    _check(hypAssignment, "Long", 1, "hypAssignment")
+    if not (_is_torch(sceneCoordinates) and sceneCoordinates.is_cuda and hypAssignment.is_cuda and pack_out.is_cuda):
+        raise RuntimeError("forward_pack takes CUDA tensors")
+    co = _Arg(sceneCoordinates)
+    aptr, astride, M, adev, _keep = _assign_arg(hypAssignment)
+    if pack_out.dtype != __import__("torch").float64 or pack_out.numel() != M + 18 or not pack_out.is_contiguous():
+        raise RuntimeError("pack_out must be a contiguous float64 tensor of M + 18 elements")
+    ctx = _pick_ctx(co.device, adev, pack_out.device.index)
+    E, _, H, W = (int(v) for v in sceneCoordinates.shape)
+    shiftX, shiftY, f, ppx, ppy, tau, alpha, beta, maxReproj, sub = params
+    ctx.check(ctx.lib.esacb200_forward_pack(ctx.handle, co.ptr, E, H, W, aptr, astride, M, int(shiftX), int(shiftY), float(f),
+                                            float(ppx), float(ppy), float(tau), float(alpha), float(beta), float(maxReproj),
+                                            int(sub), int(expert_offset), pack_out.data_ptr()))
 
 
 

@@ -55,6 +55,9 @@ struct esacb200_ctx {
     char dev_name[128] = {0};
     cudaStream_t own_stream = nullptr;
     cudaStream_t copy_stream = nullptr;
+    cudaStream_t aux_stream = nullptr;   // second lane of the sampling stage
+    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+    int sample_groups = 2;
     cudaEvent_t ev_copied[2] = {nullptr, nullptr}, ev_consumed[2] = {nullptr, nullptr};
     cudaStream_t stream = nullptr;
     uint64_t seed = 1305;  // thread_rand.h:103
@@ -236,23 +239,36 @@ int stage_inputs(esacb200_ctx* ctx, Plan& pl, const float* coords, const int64_t
 
 int run_sample(esacb200_ctx* ctx, const Plan& pl, uint64_t seed) {
     const Problem& P = pl.P;
-    const int cap = 1 << 20;
-    const int cap_acc = 1 << 16;
-    CK(ctx->smp_int.ensure(((size_t)P.M * 6 + 8) * 4 + 8));
-    CK(ctx->smp_surv.ensure((size_t)cap * sizeof(int2) + (size_t)cap_acc * sizeof(Accepted)));
-    SampleState st;
-    st.best = ctx->smp_int.as<unsigned long long>();  // 8-byte aligned: first in the buffer
+    const int cap = 1 << 19;       // per group
+    const int cap_acc = 1 << 15;
+    // two lanes pay once a wave's kernels are long enough to overlap (full-resolution maps, or very many hypotheses)
+    const int G = (ctx->sample_groups > 1 && ctx->aux_stream && P.M >= 64 && (P.N >= 65536 || P.M >= 1024)) ? 2 : 1;
+    const int Mg = (P.M + G - 1) / G;  // largest group
+    // ints: [best: 2M] [base: M] [ovf: M] then per group [list: 2*Mg] [counters: 8]
+    const size_t per_group_ints = (size_t)2 * Mg + 8;
+    CK(ctx->smp_int.ensure(((size_t)P.M * 4 + G * per_group_ints) * 4 + 8));
+    const size_t per_group_bytes = (size_t)cap * sizeof(int2) + (size_t)cap_acc * sizeof(Accepted);
+    CK(ctx->smp_surv.ensure(G * per_group_bytes));
+    SampleState st[2];
     int* b = ctx->smp_int.as<int>() + 2 * (size_t)P.M;
-    st.base = b; st.ovf = b + P.M; st.list = b + 2 * (size_t)P.M; st.counters = b + 4 * (size_t)P.M;
-    st.stage = (Accepted*)((char*)ctx->smp_surv.p + (size_t)cap * sizeof(int2));
-    st.cap_acc = cap_acc;
-    st.surv = ctx->smp_surv.as<int2>();
-    st.cap = cap;
-    st.M = P.M;
+    for (int g = 0; g < G; ++g) {
+        st[g].best = ctx->smp_int.as<unsigned long long>();  // 8-byte aligned: first in the buffer
+        st[g].base = b;
+        st[g].ovf = b + P.M;
+        st[g].list = b + 2 * (size_t)P.M + g * per_group_ints;
+        st[g].counters = st[g].list + 2 * (size_t)Mg;
+        char* sb = (char*)ctx->smp_surv.p + g * per_group_bytes;
+        st[g].surv = (int2*)sb;
+        st[g].stage = (Accepted*)(sb + (size_t)cap * sizeof(int2));
+        st[g].cap = cap;
+        st[g].cap_acc = cap_acc;
+        st[g].M = Mg;
+    }
     CK(ctx->coords4.ensure((size_t)P.E * P.N * sizeof(float4)));
     ctx->st.kernel_launches += launch_sample(pl.d_coords, ctx->coords4.as<float4>(), ctx->assign32.as<int>(), P, seed, ctx->max_tries,
-                                             ctx->inj_M ? ctx->inject.as<int>() : nullptr, ctx->inj_T, st, ctx->sm_count, ctx->sample_prefilter, ctx->hyp_offset,
-                                             ctx->poses.as<Pose>(), ctx->cells.as<int>(), ctx->tries.as<int>(), ctx->stream);
+                                             ctx->inj_M ? ctx->inject.as<int>() : nullptr, ctx->inj_T, st, G, ctx->sm_count,
+                                             ctx->sample_prefilter, ctx->hyp_offset, ctx->poses.as<Pose>(), ctx->cells.as<int>(),
+                                             ctx->tries.as<int>(), ctx->stream, ctx->aux_stream, ctx->ev_fork, ctx->ev_join);
     CK(cudaGetLastError());
     mark(ctx, EV_SAMPLE);
     return 0;
@@ -408,6 +424,13 @@ int esacb200_create(int device, esacb200_ctx** out) {
     if (cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking) != cudaSuccess) { delete ctx; return ESACB200_ERR_CUDA; }
     ctx->stream = ctx->own_stream;
     cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking);
+    {
+        int lo = 0, hi = 0;
+        cudaDeviceGetStreamPriorityRange(&lo, &hi);
+        if (cudaStreamCreateWithPriority(&ctx->aux_stream, cudaStreamNonBlocking, hi) != cudaSuccess) { ctx->aux_stream = nullptr; cudaGetLastError(); }
+        cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming);
+        cudaEventCreateWithFlags(&ctx->ev_join, cudaEventDisableTiming);
+    }
     for (int i = 0; i < 2; ++i) {
         cudaEventCreateWithFlags(&ctx->ev_copied[i], cudaEventDisableTiming);
         cudaEventCreateWithFlags(&ctx->ev_consumed[i], cudaEventDisableTiming);
@@ -443,6 +466,9 @@ void esacb200_destroy(esacb200_ctx* ctx) {
         if (ctx->ev_consumed[i]) cudaEventDestroy(ctx->ev_consumed[i]);
     }
     if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
+    if (ctx->aux_stream) cudaStreamDestroy(ctx->aux_stream);
+    if (ctx->ev_fork) cudaEventDestroy(ctx->ev_fork);
+    if (ctx->ev_join) cudaEventDestroy(ctx->ev_join);
     if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
     delete ctx;
 }
@@ -469,6 +495,7 @@ int esacb200_set_option(esacb200_ctx* ctx, const char* key, double v) {
     else if (!strcmp(key, "fixed_seed")) ctx->fixed_seed = v != 0;
     else if (!strcmp(key, "refine_group")) ctx->refine_group_opt = (int)v;
     else if (!strcmp(key, "sample_prefilter")) ctx->sample_prefilter = v != 0;
+    else if (!strcmp(key, "sample_groups")) ctx->sample_groups = v >= 2 ? 2 : 1;  // 2: two interleaved lanes on two streams
     else if (!strcmp(key, "hyp_offset")) ctx->hyp_offset = (int)v;  // global index of local hypothesis 0 (sharded runs)
     else if (!strcmp(key, "score_ppt")) ctx->score_ppt_opt = (int)v;   // 0 = automatic, else 2 / 4 / 8 cells per thread
     else if (!strcmp(key, "score_hc")) ctx->score_hc_opt = (int)v;     // 0 = automatic, else hypotheses per chunk (<= 64)
@@ -537,6 +564,34 @@ int esacb200_forward(esacb200_ctx* ctx, const float* coords, int E, int H, int W
     finish_stats(ctx);
     ctx->inj_M = ctx->inj_T = 0;
     return ESACB200_OK;
+}
+
+// -------------------------------------------------------------------------------------------------
+int esacb200_forward_pack(esacb200_ctx* ctx, const float* coords, int E, int H, int W, const int64_t* assign,
+                          int64_t assign_stride, int M, int shiftX, int shiftY, float f, float ppx, float ppy, float tau,
+                          float alpha, float beta, float maxReproj, int sub, int expert_offset, double* pack_out) {
+    if (!ctx) return ESACB200_ERR_ARG;
+    if (!coords || !assign || !pack_out) return fail(ctx, ESACB200_ERR_ARG, "null pointer argument");
+    if (!is_device_ptr(coords) || !is_device_ptr(assign) || !is_device_ptr(pack_out))
+        return fail(ctx, ESACB200_ERR_ARG, "forward_pack takes device pointers only");
+    Plan pl;
+    int rc = fill_problem(ctx, pl.P, E, H, W, M, shiftX, shiftY, f, ppx, ppy, tau, alpha, beta, maxReproj, sub);
+    if (rc) return rc;
+    if ((long long)(W - 1) * (H - 1) < 4) return fail(ctx, ESACB200_ERR_ARG, "map %dx%d too small", W, H);
+    begin_call(ctx);
+    ctx->inj_M = ctx->inj_T = 0;
+    rc = stage_inputs(ctx, pl, coords, assign, assign_stride);
+    if (rc) return rc;
+    rc = enqueue_forward_core(ctx, pl, ctx->out17.as<float>());
+    if (rc) return rc;
+    launch_pack_forward(ctx->scores.as<double>(), ctx->out17.as<float>(), M, expert_offset, pack_out, ctx->stream);
+    CK(cudaGetLastError());
+    ctx->st.kernel_launches += 1;
+    mark(ctx, EV_END);
+    ctx->st.M = M;
+    ctx->last_M = M;
+    ctx->last_backward = false;
+    return ESACB200_OK;   // stage timers of this call are not collected: that would need the synchronisation
 }
 
 // -------------------------------------------------------------------------------------------------

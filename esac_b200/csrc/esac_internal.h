@@ -109,8 +109,9 @@ struct SampleState {
 };
 // Returns the number of kernel launches it enqueued.
 int launch_sample(const float* coords, float4* coords4, const int* assign32, const Problem& P, uint64_t seed, int max_tries,
-                  const int* injected, int inj_T, const SampleState& st, int sm_count, int use_prefilter, int hyp_offset,
-                  Pose* poses, int* cells, int* tries, cudaStream_t st_);
+                  const int* injected, int inj_T, const SampleState* st, int n_groups, int sm_count, int use_prefilter,
+                  int hyp_offset, Pose* poses, int* cells, int* tries, cudaStream_t stream, cudaStream_t aux,
+                  cudaEvent_t ev_fork, cudaEvent_t ev_join);
 
 // --- refine.cu ----------------------------------------------------------------------------
 // Refines poses_in[jobs[j]] -> poses_out[jobs[j]] for j < *n_jobs (device scalar) or n_jobs_host.
@@ -139,6 +140,8 @@ int refine_max_coresident_blocks(int sm_count);
 // out[17] = bad-assignment flag, out[18] = winning hypothesis
 void launch_finish_forward(const Pose* poses, const int* winner, const int* assign32, const int* flags, float* out20,
                            cudaStream_t st);
+
+void launch_pack_forward(const double* scores, const float* out20, int M, int expert_offset, double* pack, cudaStream_t st);
 
 // --- gating.cu ----------------------------------------------------------------------------
 int assign_max_experts();

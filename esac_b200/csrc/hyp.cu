@@ -42,6 +42,7 @@ struct SampleArgs {
     int inj_T;
     int use_prefilter;    // 0: every try goes to the exact path (self-check of the prefilter)
     int hyp_offset;       // global index of local hypothesis 0 (multi-GPU shards draw the stream of the unsharded problem)
+    int h_first, h_step, Mg;  // this group's hypotheses: h_first + k * h_step, k < Mg
     SampleState st;
 };
 
@@ -83,14 +84,17 @@ __global__ void interleave_kernel(const float* __restrict__ coords, float4* __re
 }
 
 // state init: every hypothesis unresolved, window at try 0
-__global__ void sample_init_kernel(SampleState st, int M) {
-    const int h = blockIdx.x * blockDim.x + threadIdx.x;
-    if (h < M) { st.best[h] = kNoKey; st.base[h] = 0; st.ovf[h] = kNoTry; st.list[h] = h; }
-    if (h == 0) { st.counters[0] = M; st.counters[1] = 0; st.counters[2] = 0; st.counters[3] = 128; st.counters[4] = 0; }  // unresolved, survivors, staged, span, ticket
+__global__ void sample_init_kernel(SampleState st, int Mg, int h_first, int h_step) {
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k < Mg) {
+        const int h = h_first + k * h_step;
+        st.best[h] = kNoKey; st.base[h] = 0; st.ovf[h] = kNoTry; st.list[k] = h;
+    }
+    if (k == 0) { st.counters[0] = Mg; st.counters[1] = 0; st.counters[2] = 0; st.counters[3] = 128; st.counters[4] = 0; }  // unresolved, survivors, staged, span, ticket
 }
 
 // ---- wave phase 1: fp32 prefilter, one thread per try --------------------------------------------------------
-__global__ void __launch_bounds__(kTryThreads) prefilter_kernel(const __grid_constant__ SampleArgs a) {
+__global__ void __launch_bounds__(kTryThreads, 8) prefilter_kernel(const __grid_constant__ SampleArgs a) {
     const int n_unres = a.st.counters[0];
     const int span = a.st.counters[3];
     const int cph = (span + kTryThreads - 1) / kTryThreads;  // chunks per hypothesis
@@ -237,8 +241,9 @@ __global__ void __launch_bounds__(kTryThreads) tail_kernel(const __grid_constant
 
 // ---- emit: pose / cells / try count of every hypothesis ------------------------------------------------------
 __global__ void __launch_bounds__(64) emit_kernel(const __grid_constant__ SampleArgs a, Pose* poses, int* cells, int* tries) {
-    const int h = blockIdx.x * blockDim.x + threadIdx.x;
-    if (h >= a.P.M) return;
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= a.Mg) return;
+    const int h = a.h_first + k * a.h_step;
     const unsigned long long key = a.st.best[h];
     const int t = key != kNoKey ? (int)(key >> 32) : a.limit - 1;  // exhausted: the state of the last try survives (esac_util.h:154-224)
     const unsigned slot = (unsigned)(key & 0xffffffffu);
@@ -258,25 +263,42 @@ __global__ void __launch_bounds__(64) emit_kernel(const __grid_constant__ Sample
     tries[h] = t + 1;
 }
 
+// The hypotheses are dealt to n_groups (<= 2) interleaved groups, each with its own work list, survivor list, staging area
+// and stream.  A wave is a throughput-bound kernel (prefilter) followed by a latency-bound one (exact: a few thousand
+// threads, each a long fp64 dependency chain); with two groups in flight the exact kernel of one runs under the prefilter
+// of the other instead of leaving the GPU idle.
 int launch_sample(const float* coords, float4* coords4, const int* assign32, const Problem& P, uint64_t seed, int max_tries,
-                  const int* injected, int inj_T, const SampleState& st, int sm_count, int use_prefilter, int hyp_offset,
-                  Pose* poses, int* cells, int* tries, cudaStream_t stream) {
-    SampleArgs a;
-    a.coords4 = coords4; a.assign32 = assign32; a.P = P; a.seed = seed;
-    a.limit = injected ? (max_tries < inj_T ? max_tries : inj_T) : max_tries;
-    a.injected = injected; a.inj_T = inj_T; a.st = st; a.use_prefilter = use_prefilter; a.hyp_offset = hyp_offset;
+                  const int* injected, int inj_T, const SampleState* st, int n_groups, int sm_count, int use_prefilter,
+                  int hyp_offset, Pose* poses, int* cells, int* tries, cudaStream_t stream, cudaStream_t aux,
+                  cudaEvent_t ev_fork, cudaEvent_t ev_join) {
     int launches = 0;
     interleave_kernel<<<sm_count * 8, 256, 0, stream>>>(coords, coords4, P.E, P.N); ++launches;
-    sample_init_kernel<<<(P.M + 255) / 256, 256, 0, stream>>>(st, P.M); ++launches;
-    const int kWaves = 7;
-    const int grid = sm_count * 16;
-    for (int r = 0; r < kWaves; ++r) {
-        prefilter_kernel<<<grid, kTryThreads, 0, stream>>>(a); ++launches;
-        exact_kernel<<<sm_count * 4, 128, 0, stream>>>(a); ++launches;  // its last CTA also advances the windows
+    if (n_groups > 1) {
+        cudaEventRecord(ev_fork, stream);
+        cudaStreamWaitEvent(aux, ev_fork, 0);
     }
-    const int covered = 0;
-    if (covered < a.limit) { tail_kernel<<<P.M < sm_count * 4 ? P.M : sm_count * 4, kTryThreads, 0, stream>>>(a); ++launches; }
-    emit_kernel<<<(P.M + 63) / 64, 64, 0, stream>>>(a, poses, cells, tries); ++launches;
+    for (int g = 0; g < n_groups; ++g) {
+        cudaStream_t sg = g == 0 ? stream : aux;
+        SampleArgs a;
+        a.coords4 = coords4; a.assign32 = assign32; a.P = P; a.seed = seed;
+        a.limit = injected ? (max_tries < inj_T ? max_tries : inj_T) : max_tries;
+        a.injected = injected; a.inj_T = inj_T; a.st = st[g]; a.use_prefilter = use_prefilter; a.hyp_offset = hyp_offset;
+        a.h_first = g; a.h_step = n_groups; a.Mg = (P.M - g + n_groups - 1) / n_groups;
+        if (a.Mg <= 0) continue;
+        sample_init_kernel<<<(a.Mg + 255) / 256, 256, 0, sg>>>(st[g], a.Mg, a.h_first, a.h_step); ++launches;
+        const int kWaves = 7;
+        const int grid = sm_count * 16;
+        for (int r = 0; r < kWaves; ++r) {
+            prefilter_kernel<<<grid, kTryThreads, 0, sg>>>(a); ++launches;
+            exact_kernel<<<sm_count * 4, 128, 0, sg>>>(a); ++launches;  // its last CTA also advances the windows
+        }
+        tail_kernel<<<a.Mg < sm_count * 4 ? a.Mg : sm_count * 4, kTryThreads, 0, sg>>>(a); ++launches;
+        emit_kernel<<<(a.Mg + 63) / 64, 64, 0, sg>>>(a, poses, cells, tries); ++launches;
+    }
+    if (n_groups > 1) {
+        cudaEventRecord(ev_join, aux);
+        cudaStreamWaitEvent(stream, ev_join, 0);
+    }
     return launches;
 }
 

@@ -399,6 +399,23 @@ __global__ void finish_forward_kernel(const Pose* poses, const int* winner, cons
     }
 }
 
+// [scores (M) | camera pose (16) | global expert id or -1 on a bad assignment | local winner] as doubles: the record one
+// shard contributes to the all-gather of the sharded forward
+__global__ void pack_forward_kernel(const double* scores, const float* out20, int M, int expert_offset, double* pack) {
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < M + 18; i += gridDim.x * blockDim.x) {
+        double v;
+        if (i < M) v = scores[i];
+        else if (i < M + 16) v = (double)out20[i - M];
+        else if (i == M + 16) v = out20[17] != 0.f ? -1. : (double)out20[16] + (double)expert_offset;
+        else v = (double)out20[18];
+        pack[i] = v;
+    }
+}
+
+void launch_pack_forward(const double* scores, const float* out20, int M, int expert_offset, double* pack, cudaStream_t st) {
+    pack_forward_kernel<<<(M + 18 + 255) / 256, 256, 0, st>>>(scores, out20, M, expert_offset, pack);
+}
+
 void launch_finish_forward(const Pose* poses, const int* winner, const int* assign32, const int* flags, float* out20,
                            cudaStream_t st) {
     finish_forward_kernel<<<1, 32, 0, st>>>(poses, winner, assign32, flags, out20);

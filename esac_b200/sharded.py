@@ -81,18 +81,19 @@ def forward_sharded(coords_local, assign_local, out_pose, params, expert_offset:
 
     M = int(assign_local.shape[0])
     if local_forward is None:
+        if not hasattr(coords_local, "is_cuda"):
+            coords_local, assign_local = torch.from_numpy(coords_local), torch.from_numpy(assign_local)
         dev = coords_local.device if coords_local.is_cuda else torch.device("cuda", torch.cuda.current_device())
-        pose = torch.zeros(4, 4, device=dev)
+        # host inputs (the reference's callers hold CPU tensors): staged on the current stream, asynchronously if pinned
+        coords_local = coords_local.to(dev, non_blocking=True)
+        assign_local = assign_local.to(dev, non_blocking=True)
         ctx = api.context(dev.index)
         ctx.set_option("hyp_offset", hyp_offset)
+        buf = torch.empty(M + 18, dtype=torch.float64, device=dev)
         try:
-            e_local = api.forward(coords_local, assign_local, pose, *params)
+            api.forward_pack(coords_local, assign_local, params, expert_offset, buf)   # enqueued, no host sync
         finally:
             ctx.set_option("hyp_offset", 0)
-        scores = torch.empty(M, dtype=torch.float64, device=dev)
-        ctx.copy_last_scores(scores)
-        st = ctx.stats()
-        buf = pack_local(scores, pose, expert_offset + e_local, st["winner"])
     else:
         scores, pose, e_local, lw = local_forward(coords_local, assign_local, params)
         buf = pack_local(scores, pose, expert_offset + e_local, lw)
@@ -101,12 +102,19 @@ def forward_sharded(coords_local, assign_local, out_pose, params, expert_offset:
     dist.all_gather_into_tensor(gathered, buf, group=group)
     g = gathered.view(world, M + 18)
     if g.is_cuda:
-        # selection on the device, ONE small read-back: [global argmax | every rank's 18-value tail]
-        w = torch.argmax(g[:, :M].reshape(-1)).to(torch.float64).reshape(1)  # first maximum = draw(training=false)
-        small = torch.cat([w, g[:, M:].reshape(-1)]).cpu().numpy()
-        rank = int(small[0]) // M
-        tail = small[1:].reshape(world, 18)[rank]
-        gpose, expert = tail[:16].reshape(4, 4).astype(np.float32), int(tail[16])
+        # selection on the device: first maximum = draw(training=false); ONE 17-value read-back (the only host sync of the step)
+        w = torch.argmax(g[:, :M].reshape(-1))
+        tail = g.reshape(-1)[(w // M) * (M + 18) + M + torch.arange(17, device=g.device)]
+        if hasattr(out_pose, "is_cuda") and out_pose.is_cuda:
+            out_pose.copy_(tail[:16].reshape(4, 4))
+            expert = int(tail[16].item())
+            if expert < 0:
+                raise RuntimeError("hypAssignment holds an expert index outside the shard's experts")
+            return expert
+        small = tail.cpu().numpy()
+        gpose, expert = small[:16].reshape(4, 4).astype(np.float32), int(small[16])
+        if expert < 0:
+            raise RuntimeError("hypAssignment holds an expert index outside the shard's experts")
     else:
         _, _, gpose, expert, _ = select_global(g.numpy(), M)
     if hasattr(out_pose, "copy_"):

@@ -89,6 +89,19 @@ int esacb200_backward_sharded(esacb200_ctx* ctx, const float* coords, float* gra
                               float ppointY, float inlierThreshold, float inlierAlpha, float inlierBeta, float maxReproj,
                               int subSampling, esacb200_exchange_fn exchange, void* user, double* out_loss);
 
+/* The local half of a sharded esac_forward, enqueued WITHOUT a host synchronisation: runs sample -> score -> select ->
+ * refine on this shard's experts / hypotheses and writes the record the shards exchange,
+ *   pack_out[0..M)   soft-inlier scores (esac.cpp:147-150),      pack_out[M..M+16)  camera pose of the local winner,
+ *   pack_out[M+16]   expert_offset + its expert (or -1 if hypAssignment held an index outside [0,E)),
+ *   pack_out[M+17]   its local hypothesis index,
+ * as doubles into DEVICE memory, stream-ordered on the context's stream.  coords / assign must be device pointers (a host
+ * buffer would force the synchronisation this entry exists to avoid).  esac_b200/sharded.py all-gathers the records and
+ * applies softMax / draw (esac_util.h:461-530) to the concatenated scores. */
+int esacb200_forward_pack(esacb200_ctx* ctx, const float* coords, int E, int H, int W, const int64_t* assign,
+                          int64_t assign_stride, int M, int shiftX, int shiftY, float focalLength, float ppointX,
+                          float ppointY, float inlierThreshold, float inlierAlpha, float inlierBeta, float maxReproj,
+                          int subSampling, int expert_offset, double* pack_out);
+
 /* esac_forward over B images of one shape (the reference's callers loop with batch_size=1, test_esac.py:137):
  * coords float32 [B,E,3,H,W], assign int64 [B,M] (rows contiguous, element stride assign_stride; 0 = one expert for all),
  * out_poses float32 [B,4,4], out_experts int [B] (host).  One host synchronisation for the whole batch; host maps are
