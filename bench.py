@@ -235,6 +235,19 @@ def main():
     ms, ms_score, launches, score_launches, last = timed(False, args.steps, args.warmup)
     clocks = sampler.stop()
     ms_e2e, _, _, _, _ = timed(True, args.steps, args.warmup)
+    if world > 1:
+        # the sharded step enqueues the local pipeline without a host synchronisation, so it collects no stage timers;
+        # the scoring kernel's launch time (roofline) and the stage breakdown come from an untimed probe of the same local
+        # shard through the synchronising single-GPU entry
+        ms_score, score_launches = 0.0, 0
+        for i in range(12):
+            esac.forward(d_coords[i % N_SCENES], d_assign[i % N_SCENES], d_out, *params)
+            if i >= 2:
+                st = ctx.stats()
+                ms_score += st["ms_score"]
+                score_launches += st["score_launches"]
+        last = ctx.stats()
+        dist.barrier()
 
     # informative: the batched entry point (8 images per call, pinned host tensors, copy of image b+1 overlapping image b)
     batched = None

@@ -287,6 +287,9 @@ def _assign_arg(t):
     return a.ctypes.data, stride, M, None, a
 
 
+_CUDA_STREAM_LEGACY = 0x1
+
+
 def _pick_ctx(*devices) -> Context:
     devs = {d for d in devices if d is not None}
     if len(devs) > 1:
@@ -294,8 +297,11 @@ def _pick_ctx(*devices) -> Context:
     ctx = context(next(iter(devs)) if devs else None)
     stream = 0
     if devs:
+        # CUDA tensors: run on torch's current stream so that the call is ordered after whatever produced them.  torch
+        # reports its default stream as handle 0, which the C ABI reads as "use the context's own stream"; the legacy
+        # default stream has the explicit handle cudaStreamLegacy = 0x1.
         import torch
-        stream = torch.cuda.current_stream(ctx.device).cuda_stream
+        stream = torch.cuda.current_stream(ctx.device).cuda_stream or _CUDA_STREAM_LEGACY
     ctx.set_stream(stream)
     return ctx
 

@@ -131,6 +131,33 @@ def test_forward_cuda_tensors_and_stride0_assignment(api):
     assert rot < 1.0 and trans < 0.05
 
 
+def test_forward_is_ordered_after_pending_work_on_torchs_stream(api):
+    """A caller hands over expert outputs that are still being produced on torch's current stream (train_esac.py computes
+    `prediction` right before the call): the library must queue behind that work, on the default stream and on a side stream."""
+    import torch
+    sc = make_scene(E=2, H=30, W=40, M=32, sub=8, seed=9)
+    coords = torch.from_numpy(sc.coords).cuda()
+    assign = torch.from_numpy(sc.assign).cuda()
+    api.set_seed(5)
+    ref = torch.zeros(4, 4, device="cuda")
+    e_ref = api.forward(coords, assign, ref, *sc.params)
+    big = torch.randn(4096, 4096, device="cuda")
+    for stream in (None, torch.cuda.Stream()):
+        with torch.cuda.stream(stream) if stream is not None else torch.cuda.stream(torch.cuda.default_stream()):
+            late = torch.zeros_like(coords)
+            late_assign = torch.full_like(assign, 10 ** 6)          # poison: flagged as a bad expert index if read early
+            torch.cuda.synchronize()
+            for _ in range(40):                                     # ~10 ms of queued work ahead of the real inputs
+                big = big @ big * 1e-3
+            late.copy_(coords, non_blocking=True)
+            late_assign.copy_(assign, non_blocking=True)
+            api.set_seed(5)
+            out = torch.zeros(4, 4, device="cuda")
+            e = api.forward(late, late_assign, out, *sc.params)
+        torch.cuda.synchronize()
+        assert e == e_ref and torch.equal(out, ref)
+
+
 def test_forward_known_answer_noise_free(api):
     """Noise-free map: the estimate must be the ground-truth pose."""
     sc = make_scene(E=1, H=30, W=40, M=16, sub=8, seed=4, outlier_frac=0.0, noise=0.0)
