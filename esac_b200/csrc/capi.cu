@@ -58,6 +58,7 @@ struct esacb200_ctx {
     cudaStream_t aux_stream = nullptr;   // second lane of the sampling stage
     cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
     int sample_groups = 2;
+    int upload_split = 1;
     cudaEvent_t ev_copied[2] = {nullptr, nullptr}, ev_consumed[2] = {nullptr, nullptr};
     cudaStream_t stream = nullptr;
     uint64_t seed = 1305;  // thread_rand.h:103
@@ -139,6 +140,7 @@ struct Plan {
     const float* d_coords;
     const long long* d_assign;
     long long assign_stride;
+    int split_e = 0;  // > 0: host maps are uploaded in two halves [0, split_e) / [split_e, E) on the copy stream (ev_copied[0/1])
 };
 
 int fill_problem(esacb200_ctx* ctx, Problem& P, int E, int H, int W, int M, int shiftX, int shiftY, float f, float ppx,
@@ -153,11 +155,25 @@ int fill_problem(esacb200_ctx* ctx, Problem& P, int E, int H, int W, int M, int 
 
 // Upload (or alias) the inputs.  Host coordinate maps go to `cbuf` on `copy_stream` (pinned memory: asynchronous).
 int upload_inputs(esacb200_ctx* ctx, Plan& pl, const float* coords, const int64_t* assign, int64_t stride, DevBuf& cbuf,
-                  DevBuf& abuf, cudaStream_t copy_stream) {
+                  DevBuf& abuf, cudaStream_t copy_stream, bool allow_split = false) {
     const Problem& P = pl.P;
     const size_t cbytes = (size_t)P.E * 3 * P.N * sizeof(float);
+    pl.split_e = 0;
     if (is_device_ptr(coords)) {
         pl.d_coords = coords;
+    } else if (allow_split && P.E >= 2 && cbytes >= (size_t)(4 << 20) && P.M >= 64 && ctx->aux_stream && ctx->sample_groups > 1 &&
+               ctx->upload_split) {
+        // Large host maps: two halves on the copy stream, so the first half's experts are sampled while the second half is
+        // still on the wire (launch_sample deals its two lanes by expert in this case).
+        CK(cbuf.ensure(cbytes));
+        const int es = (P.E + 1) / 2;
+        const size_t first = (size_t)es * 3 * P.N * sizeof(float);
+        CK(cudaMemcpyAsync(cbuf.p, coords, first, cudaMemcpyHostToDevice, ctx->copy_stream));
+        CK(cudaEventRecord(ctx->ev_copied[0], ctx->copy_stream));
+        CK(cudaMemcpyAsync((char*)cbuf.p + first, (const char*)coords + first, cbytes - first, cudaMemcpyHostToDevice, ctx->copy_stream));
+        CK(cudaEventRecord(ctx->ev_copied[1], ctx->copy_stream));
+        pl.d_coords = cbuf.as<float>();
+        pl.split_e = es;
     } else {
         CK(cbuf.ensure(cbytes));
         CK(cudaMemcpyAsync(cbuf.p, coords, cbytes, cudaMemcpyHostToDevice, copy_stream));
@@ -224,14 +240,14 @@ int plan_and_prep(esacb200_ctx* ctx, Plan& pl) {
     int* sc = ctx->scalars.as<int>();
     launch_prep(pl.d_coords, pl.d_assign, pl.assign_stride, P, hc, ctx->assign32.as<int>(), ctx->counts.as<int>(),
                 ctx->offsets.as<int>(), ctx->perm.as<int>(), ctx->slot_of.as<int>(), ctx->chunks.as<ChunkDesc>(),
-                sc + S_NCHUNKS, sc + S_WORK, ctx->centres.as<float>(), sc + S_FLAGS, ctx->stream);
+                sc + S_NCHUNKS, sc + S_WORK, ctx->centres.as<float>(), sc + S_FLAGS, pl.split_e ? 1 : 3, ctx->stream);
     ctx->st.kernel_launches += 1;
     mark(ctx, EV_PREP);
     return 0;
 }
 
-int stage_inputs(esacb200_ctx* ctx, Plan& pl, const float* coords, const int64_t* assign, int64_t stride) {
-    int rc = upload_inputs(ctx, pl, coords, assign, stride, ctx->coords, ctx->assign64, ctx->stream);
+int stage_inputs(esacb200_ctx* ctx, Plan& pl, const float* coords, const int64_t* assign, int64_t stride, bool allow_split = false) {
+    int rc = upload_inputs(ctx, pl, coords, assign, stride, ctx->coords, ctx->assign64, ctx->stream, allow_split);
     if (rc) return rc;
     mark(ctx, EV_H2D);
     return plan_and_prep(ctx, pl);
@@ -242,8 +258,8 @@ int run_sample(esacb200_ctx* ctx, const Plan& pl, uint64_t seed) {
     const int cap = 1 << 19;       // per group
     const int cap_acc = 1 << 15;
     // two lanes pay once a wave's kernels are long enough to overlap (full-resolution maps, or very many hypotheses)
-    const int G = (ctx->sample_groups > 1 && ctx->aux_stream && P.M >= 64 && (P.N >= 65536 || P.M >= 1024)) ? 2 : 1;
-    const int Mg = (P.M + G - 1) / G;  // largest group
+    const int G = pl.split_e ? 2 : ((ctx->sample_groups > 1 && ctx->aux_stream && P.M >= 64 && (P.N >= 65536 || P.M >= 1024)) ? 2 : 1);
+    const int Mg = pl.split_e ? P.M : (P.M + G - 1) / G;  // capacity of a lane's work list
     // ints: [best: 2M] [base: M] [ovf: M] then per group [list: 2*Mg] [counters: 8]
     const size_t per_group_ints = (size_t)2 * Mg + 8;
     CK(ctx->smp_int.ensure(((size_t)P.M * 4 + G * per_group_ints) * 4 + 8));
@@ -268,8 +284,17 @@ int run_sample(esacb200_ctx* ctx, const Plan& pl, uint64_t seed) {
     ctx->st.kernel_launches += launch_sample(pl.d_coords, ctx->coords4.as<float4>(), ctx->assign32.as<int>(), P, seed, ctx->max_tries,
                                              ctx->inj_M ? ctx->inject.as<int>() : nullptr, ctx->inj_T, st, G, ctx->sm_count,
                                              ctx->sample_prefilter, ctx->hyp_offset, ctx->poses.as<Pose>(), ctx->cells.as<int>(),
-                                             ctx->tries.as<int>(), ctx->stream, ctx->aux_stream, ctx->ev_fork, ctx->ev_join);
+                                             ctx->tries.as<int>(), ctx->stream, ctx->aux_stream, ctx->ev_fork, ctx->ev_join,
+                                             pl.split_e, ctx->perm.as<int>(), ctx->offsets.as<int>(), ctx->ev_copied);
     CK(cudaGetLastError());
+    if (pl.split_e) {
+        // both halves have landed (the join orders this stream after lane 1, which waited for the second half): plane centres
+        int* sc = ctx->scalars.as<int>();
+        launch_prep(pl.d_coords, pl.d_assign, pl.assign_stride, P, pl.hc, ctx->assign32.as<int>(), ctx->counts.as<int>(),
+                    ctx->offsets.as<int>(), ctx->perm.as<int>(), ctx->slot_of.as<int>(), ctx->chunks.as<ChunkDesc>(),
+                    sc + S_NCHUNKS, sc + S_WORK, ctx->centres.as<float>(), sc + S_FLAGS, 2, ctx->stream);
+        ctx->st.kernel_launches += 1;
+    }
     mark(ctx, EV_SAMPLE);
     return 0;
 }
@@ -495,6 +520,7 @@ int esacb200_set_option(esacb200_ctx* ctx, const char* key, double v) {
     else if (!strcmp(key, "fixed_seed")) ctx->fixed_seed = v != 0;
     else if (!strcmp(key, "refine_group")) ctx->refine_group_opt = (int)v;
     else if (!strcmp(key, "sample_prefilter")) ctx->sample_prefilter = v != 0;
+    else if (!strcmp(key, "upload_split")) ctx->upload_split = v != 0;  // host maps in two halves, sampling under the second copy
     else if (!strcmp(key, "sample_groups")) ctx->sample_groups = v >= 2 ? 2 : 1;  // 2: two interleaved lanes on two streams
     else if (!strcmp(key, "hyp_offset")) ctx->hyp_offset = (int)v;  // global index of local hypothesis 0 (sharded runs)
     else if (!strcmp(key, "score_ppt")) ctx->score_ppt_opt = (int)v;   // 0 = automatic, else 2 / 4 / 8 cells per thread
@@ -536,7 +562,7 @@ int esacb200_forward(esacb200_ctx* ctx, const float* coords, int E, int H, int W
     if ((long long)(W - 1) * (H - 1) < 4) return fail(ctx, ESACB200_ERR_ARG, "map %dx%d too small to draw 4 distinct cells from [0,W-2]x[0,H-2]", W, H);
     if (ctx->inj_M && ctx->inj_M != M) return fail(ctx, ESACB200_ERR_ARG, "injected cells are for M=%d, call has M=%d", ctx->inj_M, M);
     begin_call(ctx);
-    rc = stage_inputs(ctx, pl, coords, assign, assign_stride);
+    rc = stage_inputs(ctx, pl, coords, assign, assign_stride, /*allow_split=*/!ctx->inj_M);
     if (rc) return rc;
     const Problem& P = pl.P;
     int* sc = ctx->scalars.as<int>();

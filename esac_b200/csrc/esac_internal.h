@@ -74,9 +74,9 @@ struct ScoreArgs {
 // --- score.cu -----------------------------------------------------------------------------
 // prep: int64 strided assignment -> int32, per-expert histogram / offsets / stable permutation,
 // chunk table, work counter reset, plane centres.  flags[0] != 0 on a bad expert index.
-void launch_prep(const float* coords, const long long* assign, long long assign_stride, const Problem& P,
-                 int hc, int* assign32, int* counts, int* offsets, int* perm, int* slot_of, ChunkDesc* chunks,
-                 int* n_chunks, int* work_counter, float* centres, int* flags, cudaStream_t st);
+void launch_prep(const float* coords, const long long* assign, long long assign_stride, const Problem& P, int hc,
+                 int* assign32, int* counts, int* offsets, int* perm, int* slot_of, ChunkDesc* chunks, int* n_chunks,
+                 int* work_counter, float* centres, int* flags, int roles, cudaStream_t st);
 void launch_fold(const Pose* poses, const int* perm, const int* assign32, const float* centres, const Problem& P,
                  PosePk* out, cudaStream_t st);
 int score_tile_pixels(int ppt);
@@ -109,9 +109,10 @@ struct SampleState {
 };
 // Returns the number of kernel launches it enqueued.
 int launch_sample(const float* coords, float4* coords4, const int* assign32, const Problem& P, uint64_t seed, int max_tries,
-                  const int* injected, int inj_T, const SampleState* st, int n_groups, int sm_count, int use_prefilter,
+                  const int* injected, int inj_T, const SampleState* st, int n_lanes, int sm_count, int use_prefilter,
                   int hyp_offset, Pose* poses, int* cells, int* tries, cudaStream_t stream, cudaStream_t aux,
-                  cudaEvent_t ev_fork, cudaEvent_t ev_join);
+                  cudaEvent_t ev_fork, cudaEvent_t ev_join, int split_e, const int* perm, const int* offsets,
+                  const cudaEvent_t* ev_half);
 
 // --- refine.cu ----------------------------------------------------------------------------
 // Refines poses_in[jobs[j]] -> poses_out[jobs[j]] for j < *n_jobs (device scalar) or n_jobs_host.

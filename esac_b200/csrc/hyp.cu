@@ -42,9 +42,20 @@ struct SampleArgs {
     int inj_T;
     int use_prefilter;    // 0: every try goes to the exact path (self-check of the prefilter)
     int hyp_offset;       // global index of local hypothesis 0 (multi-GPU shards draw the stream of the unsharded problem)
-    int h_first, h_step, Mg;  // this group's hypotheses: h_first + k * h_step, k < Mg
+    int h_first, h_step, Mg;  // this lane's hypotheses: h_first + k * h_step, k < Mg ...
+    const int* perm;          // ... or, when set, the hypotheses of experts [e_lo, e_hi): perm[offsets[e_lo] + k]
+    const int* offsets;
+    int e_lo, e_hi;
     SampleState st;
 };
+
+// k-th hypothesis of the lane and the lane's size
+__device__ __forceinline__ int lane_size(const SampleArgs& a) {
+    return a.perm ? a.offsets[a.e_hi] - a.offsets[a.e_lo] : a.Mg;
+}
+__device__ __forceinline__ int lane_hyp(const SampleArgs& a, int k) {
+    return a.perm ? a.perm[a.offsets[a.e_lo] + k] : a.h_first + k * a.h_step;
+}
 
 __device__ __forceinline__ void load_try(const SampleArgs& a, int h, int t, int cx[4], int cy[4], float obj[4][3], float img[4][2]) {
     const Problem& P = a.P;
@@ -84,13 +95,15 @@ __global__ void interleave_kernel(const float* __restrict__ coords, float4* __re
 }
 
 // state init: every hypothesis unresolved, window at try 0
-__global__ void sample_init_kernel(SampleState st, int Mg, int h_first, int h_step) {
+__global__ void sample_init_kernel(const __grid_constant__ SampleArgs a) {
+    const SampleState& st = a.st;
     const int k = blockIdx.x * blockDim.x + threadIdx.x;
-    if (k < Mg) {
-        const int h = h_first + k * h_step;
+    const int n = lane_size(a);
+    if (k < n) {
+        const int h = lane_hyp(a, k);
         st.best[h] = kNoKey; st.base[h] = 0; st.ovf[h] = kNoTry; st.list[k] = h;
     }
-    if (k == 0) { st.counters[0] = Mg; st.counters[1] = 0; st.counters[2] = 0; st.counters[3] = 128; st.counters[4] = 0; }  // unresolved, survivors, staged, span, ticket
+    if (k == 0) { st.counters[0] = n; st.counters[1] = 0; st.counters[2] = 0; st.counters[3] = 128; st.counters[4] = 0; }  // unresolved, survivors, staged, span, ticket
 }
 
 // ---- wave phase 1: fp32 prefilter, one thread per try --------------------------------------------------------
@@ -242,8 +255,8 @@ __global__ void __launch_bounds__(kTryThreads) tail_kernel(const __grid_constant
 // ---- emit: pose / cells / try count of every hypothesis ------------------------------------------------------
 __global__ void __launch_bounds__(64) emit_kernel(const __grid_constant__ SampleArgs a, Pose* poses, int* cells, int* tries) {
     const int k = blockIdx.x * blockDim.x + threadIdx.x;
-    if (k >= a.Mg) return;
-    const int h = a.h_first + k * a.h_step;
+    if (k >= lane_size(a)) return;
+    const int h = lane_hyp(a, k);
     const unsigned long long key = a.st.best[h];
     const int t = key != kNoKey ? (int)(key >> 32) : a.limit - 1;  // exhausted: the state of the last try survives (esac_util.h:154-224)
     const unsigned slot = (unsigned)(key & 0xffffffffu);
@@ -263,39 +276,54 @@ __global__ void __launch_bounds__(64) emit_kernel(const __grid_constant__ Sample
     tries[h] = t + 1;
 }
 
-// The hypotheses are dealt to n_groups (<= 2) interleaved groups, each with its own work list, survivor list, staging area
-// and stream.  A wave is a throughput-bound kernel (prefilter) followed by a latency-bound one (exact: a few thousand
-// threads, each a long fp64 dependency chain); with two groups in flight the exact kernel of one runs under the prefilter
-// of the other instead of leaving the GPU idle.
+// The hypotheses are dealt to n_lanes (<= 2) lanes, each with its own work list, survivor list, staging area and stream.
+// A wave is a throughput-bound kernel (prefilter) followed by a latency-bound one (exact: a few thousand threads, each a
+// long fp64 dependency chain); with two lanes in flight the exact kernel of one runs under the prefilter of the other
+// instead of leaving the GPU idle.  Lanes are dealt by hypothesis parity, or -- when the coordinate maps are still
+// arriving from the host in two halves (split_e > 0) -- by expert: lane 0 = experts [0, split_e), released by
+// ev_half[0]; lane 1 = the rest, released by ev_half[1], so lane 0 samples while the second half is on the wire.
 int launch_sample(const float* coords, float4* coords4, const int* assign32, const Problem& P, uint64_t seed, int max_tries,
-                  const int* injected, int inj_T, const SampleState* st, int n_groups, int sm_count, int use_prefilter,
+                  const int* injected, int inj_T, const SampleState* st, int n_lanes, int sm_count, int use_prefilter,
                   int hyp_offset, Pose* poses, int* cells, int* tries, cudaStream_t stream, cudaStream_t aux,
-                  cudaEvent_t ev_fork, cudaEvent_t ev_join) {
+                  cudaEvent_t ev_fork, cudaEvent_t ev_join, int split_e, const int* perm, const int* offsets,
+                  const cudaEvent_t* ev_half) {
     int launches = 0;
-    interleave_kernel<<<sm_count * 8, 256, 0, stream>>>(coords, coords4, P.E, P.N); ++launches;
-    if (n_groups > 1) {
+    if (!split_e) { interleave_kernel<<<sm_count * 8, 256, 0, stream>>>(coords, coords4, P.E, P.N); ++launches; }
+    if (n_lanes > 1) {
         cudaEventRecord(ev_fork, stream);
         cudaStreamWaitEvent(aux, ev_fork, 0);
     }
-    for (int g = 0; g < n_groups; ++g) {
+    for (int g = 0; g < n_lanes; ++g) {
         cudaStream_t sg = g == 0 ? stream : aux;
         SampleArgs a;
         a.coords4 = coords4; a.assign32 = assign32; a.P = P; a.seed = seed;
         a.limit = injected ? (max_tries < inj_T ? max_tries : inj_T) : max_tries;
         a.injected = injected; a.inj_T = inj_T; a.st = st[g]; a.use_prefilter = use_prefilter; a.hyp_offset = hyp_offset;
-        a.h_first = g; a.h_step = n_groups; a.Mg = (P.M - g + n_groups - 1) / n_groups;
-        if (a.Mg <= 0) continue;
-        sample_init_kernel<<<(a.Mg + 255) / 256, 256, 0, sg>>>(st[g], a.Mg, a.h_first, a.h_step); ++launches;
+        a.h_first = g; a.h_step = n_lanes; a.Mg = (P.M - g + n_lanes - 1) / n_lanes;
+        a.perm = nullptr; a.offsets = nullptr; a.e_lo = a.e_hi = 0;
+        int bound = a.Mg;  // host-side bound on the lane size (grid sizing)
+        if (split_e) {
+            a.perm = perm; a.offsets = offsets;
+            a.e_lo = g == 0 ? 0 : split_e;
+            a.e_hi = g == 0 ? split_e : P.E;
+            bound = P.M;
+            cudaStreamWaitEvent(sg, ev_half[g], 0);
+            const int ne = a.e_hi - a.e_lo;
+            interleave_kernel<<<sm_count * 8, 256, 0, sg>>>(coords + (size_t)a.e_lo * 3 * P.N, coords4 + (size_t)a.e_lo * P.N, ne, P.N);
+            ++launches;
+        }
+        if (bound <= 0) continue;
+        sample_init_kernel<<<(bound + 255) / 256, 256, 0, sg>>>(a); ++launches;
         const int kWaves = 7;
         const int grid = sm_count * 16;
         for (int r = 0; r < kWaves; ++r) {
             prefilter_kernel<<<grid, kTryThreads, 0, sg>>>(a); ++launches;
             exact_kernel<<<sm_count * 4, 128, 0, sg>>>(a); ++launches;  // its last CTA also advances the windows
         }
-        tail_kernel<<<a.Mg < sm_count * 4 ? a.Mg : sm_count * 4, kTryThreads, 0, sg>>>(a); ++launches;
-        emit_kernel<<<(a.Mg + 63) / 64, 64, 0, sg>>>(a, poses, cells, tries); ++launches;
+        tail_kernel<<<bound < sm_count * 4 ? bound : sm_count * 4, kTryThreads, 0, sg>>>(a); ++launches;
+        emit_kernel<<<(bound + 63) / 64, 64, 0, sg>>>(a, poses, cells, tries); ++launches;
     }
-    if (n_groups > 1) {
+    if (n_lanes > 1) {
         cudaEventRecord(ev_join, aux);
         cudaStreamWaitEvent(stream, ev_join, 0);
     }

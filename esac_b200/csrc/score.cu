@@ -25,9 +25,13 @@ constexpr int kScoreThreads = 256;
 __global__ void __launch_bounds__(1024) prep_kernel(const float* __restrict__ coords, const long long* __restrict__ assign,
                                                     long long stride, Problem P, int hc, int* assign32, int* counts,
                                                     int* offsets, int* perm, int* slot_of, ChunkDesc* chunks,
-                                                    int* n_chunks, int* work_counter, float* centres, int* flags) {
+                                                    int* n_chunks, int* work_counter, float* centres, int* flags,
+                                                    int with_assign) {
+    // block 0 (when with_assign): the assignment bookkeeping; every other block: the centre of one expert's plane.  The two
+    // roles can be launched separately (with_assign = 1 and no centre blocks / with_assign = 0) when the planes are still
+    // on their way from the host.
     const int tid = threadIdx.x;
-    if (blockIdx.x == 0) {
+    if (with_assign && blockIdx.x == 0) {
         if (tid == 0) { *work_counter = 0; flags[0] = 0; }
         for (int e = tid; e < P.E; e += blockDim.x) counts[e] = 0;
         __syncthreads();
@@ -74,7 +78,7 @@ __global__ void __launch_bounds__(1024) prep_kernel(const float* __restrict__ co
         }
     } else {
         // plane centre: mean of a strided sample (only conditions the fp32 arithmetic)
-        const int e = blockIdx.x - 1;
+        const int e = blockIdx.x - with_assign;
         const float* pl = coords + (size_t)e * 3 * P.N;
         const int ns = min(P.N, 4096);
         const int step = max(1, P.N / ns);
@@ -104,11 +108,14 @@ __global__ void __launch_bounds__(1024) prep_kernel(const float* __restrict__ co
     }
 }
 
+// roles: bit 0 = assignment bookkeeping, bit 1 = plane centres
 void launch_prep(const float* coords, const long long* assign, long long assign_stride, const Problem& P, int hc,
                  int* assign32, int* counts, int* offsets, int* perm, int* slot_of, ChunkDesc* chunks, int* n_chunks,
-                 int* work_counter, float* centres, int* flags, cudaStream_t st) {
-    prep_kernel<<<1 + P.E, 1024, 0, st>>>(coords, assign, assign_stride, P, hc, assign32, counts, offsets, perm, slot_of,
-                                          chunks, n_chunks, work_counter, centres, flags);
+                 int* work_counter, float* centres, int* flags, int roles, cudaStream_t st) {
+    const int with_assign = roles & 1, n_centres = (roles & 2) ? P.E : 0;
+    if (with_assign + n_centres == 0) return;
+    prep_kernel<<<with_assign + n_centres, 1024, 0, st>>>(coords, assign, assign_stride, P, hc, assign32, counts, offsets, perm,
+                                                          slot_of, chunks, n_chunks, work_counter, centres, flags, with_assign);
 }
 
 // ---------------------------------------------------------------------------------------------

@@ -84,3 +84,32 @@ def test_forward_is_reproducible_and_winner_is_local_argmax(api, scene):
     assert outs[0][0] == sc.gt_expert
     rot, trans = pose_error(outs[0][1], sc.gt_pose)
     assert rot < 0.1 and trans < 0.01
+
+
+@pytest.mark.parametrize("kw", [dict(E=7, M=256, per_expert=True), dict(E=3, M=200), dict(E=2, M=64, gt_mass=1.0)])
+def test_split_upload_of_host_maps_changes_nothing(api, kw):
+    """Host maps >= 4 MB are uploaded in two halves with the first half's experts sampled under the second copy
+    (lanes dealt by expert).  Scores, sampled sets, winner and pose must equal the plain path, CPU tensors and CUDA tensors
+    alike; an expert half without any hypothesis (gt_mass = 1) is an empty lane."""
+    import torch
+    sc = make_scene(H=480, W=640, sub=1, seed=31, active_only=False, **kw)
+    ctx = api.context()
+    res = {}
+    for mode in ("split", "plain", "cuda"):
+        ctx.set_option("upload_split", 1 if mode == "split" else 0)
+        api.set_seed(77)
+        if mode == "cuda":
+            out = torch.zeros(4, 4, device="cuda")
+            e = api.forward(torch.from_numpy(sc.coords).cuda(), torch.from_numpy(sc.assign).cuda(), out, *sc.params)
+            out = out.cpu().numpy()
+        else:
+            out = np.zeros((4, 4), np.float32)
+            e = api.forward(torch.from_numpy(sc.coords).pin_memory(), torch.from_numpy(sc.assign), torch.from_numpy(out), *sc.params)
+        hy = api.last_hypotheses()
+        res[mode] = (e, out.copy(), hy["scores"].copy(), hy["cells"].copy(), hy["tries"].copy())
+    ctx.set_option("upload_split", 1)
+    for mode in ("plain", "cuda"):
+        assert res["split"][0] == res[mode][0]
+        assert np.array_equal(res["split"][1], res[mode][1])
+        assert np.array_equal(res["split"][3], res[mode][3]) and np.array_equal(res["split"][4], res[mode][4])
+        assert np.array_equal(res["split"][2], res[mode][2])
