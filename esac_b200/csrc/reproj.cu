@@ -271,12 +271,13 @@ __global__ void __launch_bounds__(kThreads, 5) reproj_kernel(const float* __rest
 
 int reproj_blocks_per_image(int N, int B, int sm_count) {
     // Many short CTAs (each a few KB of traffic) rather than one resident wave: the hardware scheduler then keeps every SM
-    // streaming to the end, where a persistent grid of sm_count * k CTAs would finish with a ragged tail.  Two passes per
-    // CTA at most, so the count stays a pure function of N (the fixed summation order depends on it).
+    // streaming to the end, where a persistent grid of sm_count * k CTAs would finish with a ragged tail.  Two passes per CTA
+    // on large maps amortise the per-CTA prologue / reduction; the count is a pure function of N (the fixed summation
+    // order depends on it).
     (void)B; (void)sm_count;
     const int per_block = kThreads * kCellsPerThread;
     const int need = (N + per_block - 1) / per_block;
-    return need <= 1024 ? need : (need + 1) / 2;
+    return need < 64 ? need : (need < 256 ? (need + 1) / 2 : (need + 3) / 4);
 }
 
 void launch_reproj(const float* coords, float* grads, const float* img, int B, int N, int W, float sub, float f, float cx,
