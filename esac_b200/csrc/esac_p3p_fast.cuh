@@ -62,8 +62,11 @@ ESAC_HD bool fast_line_conic(const FastLine& L, float d00, float d01, float d02,
 }
 
 // Returns false only when the try certainly fails the 4-point gate.
+constexpr float kPrefilterMargin = 2.f;    // 4th-point error band, in units of tau, inside which the exact path decides (MC: no false reject down to 1.5)
+constexpr float kPrefilterNeedle = 0.02f;  // shortest / longest squared side below which the triangle goes to the exact path
+
 ESAC_HD bool p3p_may_pass_fast(const float obj[4][3], const float img[4][2], float f, float ppx, float ppy, float tau,
-                               float margin = 4.f) {
+                               float margin = kPrefilterMargin, float needle = kPrefilterNeedle) {
     using N = Num<float>;
     // ---- bearings, recentred scene points --------------------------------------------------------------------
     float y[3][3], x1[3], x2[3], x3[3];
@@ -86,7 +89,7 @@ ESAC_HD bool p3p_may_pass_fast(const float obj[4][3], const float img[4][2], flo
     const float c13 = y[0][0] * y[2][0] + y[0][1] * y[2][1] + y[0][2] * y[2][2];
     const float c23 = y[1][0] * y[2][0] + y[1][1] * y[2][1] + y[1][2] * y[2][2];
     const float cm = fmaxf(fabsf(c12), fmaxf(fabsf(c13), fabsf(c23)));
-    if (amin < 0.02f * amax || cm > 0.9999f) return true;  // needle triangle / nearly parallel bearings
+    if (amin < needle * amax || cm > 0.9999f) return true;  // needle triangle / nearly parallel bearings
     const float iam = N::div_(1.f, amax);
     const float s12 = a12 * iam, s13 = a13 * iam, s23 = a23 * iam;
     // ---- the two conics (symmetric storage 00 01 02 11 12 22) ------------------------------------------------

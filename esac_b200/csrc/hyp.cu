@@ -10,7 +10,7 @@
 //   device from the acceptance rate seen so far, ~1.25 / p, so that ~70% of the remaining hypotheses resolve per
 //   wave and < 2x the necessary tries are evaluated):
 //     prefilter_kernel   one thread per try, fp32 only: p3p_may_pass() discards tries whose every P3P root misses
-//                        the 4th point by > 4 tau (>95% on wrong experts); survivors are appended to a global list
+//                        the 4th point by > 2 tau (>96% on wrong experts); survivors are appended to a global list
 //     exact_kernel       one thread per survivor: the fp64 path (p3p_pose + minimal_set_gate) whose verdict is the
 //                        only one that counts; atomicMin keeps the lowest accepted try per hypothesis
 //     (advance)          the last CTA of exact_kernel marks resolved hypotheses, advances the window of the others and

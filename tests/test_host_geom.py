@@ -221,7 +221,7 @@ def test_float_prefilter_never_rejects_an_accepted_try(lib, kw, which):
                 break
         obj = np.ascontiguousarray(pl[:, ys, xs].T.astype(np.float32))
         img = np.ascontiguousarray(np.stack([xs * 8 + 4, ys * 8 + 4], 1).astype(np.float32))
-        lib.esacb200_host_try(_ptr(obj), _ptr(img), sc.f, sc.ppx, sc.ppy, sc.tau, 4.0, C.byref(mp), C.byref(ac))
+        lib.esacb200_host_try(_ptr(obj), _ptr(img), sc.f, sc.ppx, sc.ppy, sc.tau, 2.0, C.byref(mp), C.byref(ac))  # 2.0 = kPrefilterMargin, the shipping band
         assert not (ac.value and not mp.value)
         n_acc += ac.value; n_may += mp.value
     if which == "gt":
