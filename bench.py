@@ -302,6 +302,13 @@ def main():
         alg_bytes = M_local * 12.0 * N  # per scoring launch on this rank
         t_score = ms_score / max(score_launches, 1) * 1e-3
         achieved = alg_bytes / t_score / 1e9 if t_score > 0 else 0.0
+        # the resource that actually binds the kernel: 3 MUFU ops per cell-hypothesis at 16 lanes/clk/SM (profiles/r01_pipes.txt)
+        sm_count = api.context(local_rank).device_info()["sm_count"]
+        mhz = (clocks or {}).get("sm_mhz") or 1965.0
+        mufu_peak = sm_count * (16.0 / 3.0) * mhz * 1e6 / N  # hypotheses/s
+        on_chip = {"pipe": "MUFU (rsqrt, ex2, rcp per cell-hypothesis; 16 lanes/clk/SM measured)", "peak_hyps_per_s": mufu_peak,
+                   "achieved_hyps_per_s": M_local / t_score if t_score > 0 else None,
+                   "frac": (M_local / t_score) / mufu_peak if t_score > 0 else None}
         traffic = None
         tp = ROOT / "profiles" / "score_kernel_traffic.json"
         if tp.exists():
@@ -321,7 +328,8 @@ def main():
                              "algorithmic_bytes_per_launch": alg_bytes, "ms_per_launch": t_score * 1e3,
                              "hyps_per_s_kernel_only": M_local / t_score if t_score > 0 else None,
                              "note": "achieved = hypotheses x 12 B x 307200 cells / CUDA-event time of the scoring launch; "
-                                     "each plane is read once per 64-hypothesis chunk, so frac > 1 is expected"},
+                                     "each plane is read once per 64-hypothesis chunk, so frac > 1 is expected",
+                             "on_chip_ceiling": on_chip},
                 "stages_ms_last_step": {k: last[k] for k in ("ms_h2d", "ms_prep", "ms_sample", "ms_score", "ms_select",
                                                               "ms_refine", "ms_total")},
                 "score_launch": {"ppt": last["score_ppt"], "grid": last["score_grid"], "refine_group": last["refine_group"]}}

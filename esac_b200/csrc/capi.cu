@@ -335,7 +335,9 @@ int run_score(esacb200_ctx* ctx, const Plan& pl) {
 int pick_group(esacb200_ctx* ctx, const Problem& P, int jobs_hint) {
     if (ctx->refine_group_opt > 0) return ctx->refine_group_opt < ctx->refine_coresident ? ctx->refine_group_opt : ctx->refine_coresident;
     const int words = (P.N + 31) / 32;
-    int g = words / 100;  // ~96 CTAs at 480x640: best of the measured sweep (profiles/r01e_refine_groups.txt)
+    // ~320 cells per CTA, up to every co-resident CTA: with the warp-parallel slot summation the inter-CTA barrier costs less
+    // than the fp64 work it spreads, at every shape measured (profiles/r01m_refine_groups.txt: 60x80 -> 16, 480x640 -> 148)
+    int g = words / 10;
     if (g < 1) g = 1;
     int cap = ctx->refine_coresident / (jobs_hint > 0 ? jobs_hint : 1);
     if (cap < 1) cap = 1;
