@@ -9,6 +9,8 @@
 #include <stdlib.h>
 #include <string.h>
 
+#include <exception>
+#include <new>
 #include <vector>
 #include <thread>
 #include <chrono>
@@ -430,6 +432,16 @@ void finish_stats(esacb200_ctx* ctx) {
 
 }  // namespace
 
+// No C++ exception may cross the C ABI (std::vector / std::thread can throw): every entry point that allocates on the host is
+// a function-try-block ending in this handler.
+#define ESAC_ABI_CATCH(ctx)                                                                                   \
+    catch (const std::exception& e) {                                                                         \
+        return (ctx) ? fail((ctx), ESACB200_ERR_ARG, "host-side failure: %s", e.what()) : ESACB200_ERR_ARG;   \
+    }                                                                                                         \
+    catch (...) {                                                                                             \
+        return (ctx) ? fail((ctx), ESACB200_ERR_ARG, "host-side failure (unknown exception)") : ESACB200_ERR_ARG; \
+    }
+
 // =================================================================================================
 extern "C" {
 
@@ -441,7 +453,8 @@ int esacb200_create(int device, esacb200_ctx** out) {
         cudaGetLastError();
         return ESACB200_ERR_NO_DEVICE;
     }
-    esacb200_ctx* ctx = new esacb200_ctx();
+    esacb200_ctx* ctx = new (std::nothrow) esacb200_ctx();
+    if (!ctx) return ESACB200_ERR_ARG;
     ctx->device = device;
     if (cudaSetDevice(device) != cudaSuccess) { delete ctx; return ESACB200_ERR_NO_DEVICE; }
     cudaDeviceProp prop;
@@ -532,7 +545,7 @@ int esacb200_set_option(esacb200_ctx* ctx, const char* key, double v) {
     return ESACB200_OK;
 }
 
-int esacb200_inject_cells(esacb200_ctx* ctx, const int32_t* cells, int M, int T) {
+int esacb200_inject_cells(esacb200_ctx* ctx, const int32_t* cells, int M, int T) try {
     if (!ctx) return ESACB200_ERR_ARG;
     cudaSetDevice(ctx->device);
     if (!cells) { ctx->inj_M = ctx->inj_T = 0; return ESACB200_OK; }
@@ -543,7 +556,7 @@ int esacb200_inject_cells(esacb200_ctx* ctx, const int32_t* cells, int M, int T)
     ctx->inj_M = M;
     ctx->inj_T = T;
     return ESACB200_OK;
-}
+} ESAC_ABI_CATCH(ctx)
 
 int esacb200_device_info(esacb200_ctx* ctx, int* sm_count, char* name, int name_len) {
     if (!ctx) return ESACB200_ERR_ARG;
@@ -555,7 +568,7 @@ int esacb200_device_info(esacb200_ctx* ctx, int* sm_count, char* name, int name_
 // -------------------------------------------------------------------------------------------------
 int esacb200_forward(esacb200_ctx* ctx, const float* coords, int E, int H, int W, const int64_t* assign,
                      int64_t assign_stride, int M, float* out_pose, int shiftX, int shiftY, float f, float ppx,
-                     float ppy, float tau, float alpha, float beta, float maxReproj, int sub, int* out_expert) {
+                     float ppy, float tau, float alpha, float beta, float maxReproj, int sub, int* out_expert) try {
     if (!ctx) return ESACB200_ERR_ARG;
     if (!coords || !assign || !out_pose) return fail(ctx, ESACB200_ERR_ARG, "null pointer argument");
     Plan pl;
@@ -592,12 +605,12 @@ int esacb200_forward(esacb200_ctx* ctx, const float* coords, int E, int H, int W
     finish_stats(ctx);
     ctx->inj_M = ctx->inj_T = 0;
     return ESACB200_OK;
-}
+} ESAC_ABI_CATCH(ctx)
 
 // -------------------------------------------------------------------------------------------------
 int esacb200_forward_pack(esacb200_ctx* ctx, const float* coords, int E, int H, int W, const int64_t* assign,
                           int64_t assign_stride, int M, int shiftX, int shiftY, float f, float ppx, float ppy, float tau,
-                          float alpha, float beta, float maxReproj, int sub, int expert_offset, double* pack_out) {
+                          float alpha, float beta, float maxReproj, int sub, int expert_offset, double* pack_out) try {
     if (!ctx) return ESACB200_ERR_ARG;
     if (!coords || !assign || !pack_out) return fail(ctx, ESACB200_ERR_ARG, "null pointer argument");
     if (!is_device_ptr(coords) || !is_device_ptr(assign) || !is_device_ptr(pack_out))
@@ -620,7 +633,7 @@ int esacb200_forward_pack(esacb200_ctx* ctx, const float* coords, int E, int H, 
     ctx->last_M = M;
     ctx->last_backward = false;
     return ESACB200_OK;   // stage timers of this call are not collected: that would need the synchronisation
-}
+} ESAC_ABI_CATCH(ctx)
 
 // -------------------------------------------------------------------------------------------------
 // esac_forward over a batch of B images of one shape (BASELINE configs[2]: "batch 8 images").  The reference has no such
@@ -629,7 +642,7 @@ int esacb200_forward_pack(esacb200_ctx* ctx, const float* coords, int E, int H, 
 // second stream so the copy of image b+1 overlaps the kernels of image b.
 int esacb200_forward_batch(esacb200_ctx* ctx, int B, const float* coords, int E, int H, int W, const int64_t* assign,
                            int64_t assign_stride, int M, float* out_poses, int shiftX, int shiftY, float f, float ppx,
-                           float ppy, float tau, float alpha, float beta, float maxReproj, int sub, int* out_experts) {
+                           float ppy, float tau, float alpha, float beta, float maxReproj, int sub, int* out_experts) try {
     if (!ctx) return ESACB200_ERR_ARG;
     if (!coords || !assign || !out_poses || B <= 0) return fail(ctx, ESACB200_ERR_ARG, "null pointer argument or empty batch");
     Plan pl;
@@ -685,12 +698,12 @@ int esacb200_forward_batch(esacb200_ctx* ctx, int B, const float* coords, int E,
     ctx->last_backward = false;
     finish_stats(ctx);
     return ESACB200_OK;
-}
+} ESAC_ABI_CATCH(ctx)
 
 // -------------------------------------------------------------------------------------------------
 int esacb200_score_poses(esacb200_ctx* ctx, const float* coords, int E, int H, int W, const int64_t* assign,
                          int64_t assign_stride, int M, const double* poses6, int shiftX, int shiftY, float f, float ppx,
-                         float ppy, float tau, float alpha, float beta, float maxReproj, int sub, double* out_scores) {
+                         float ppy, float tau, float alpha, float beta, float maxReproj, int sub, double* out_scores) try {
     if (!ctx) return ESACB200_ERR_ARG;
     if (!coords || !assign || !poses6 || !out_scores) return fail(ctx, ESACB200_ERR_ARG, "null pointer argument");
     Plan pl;
@@ -717,12 +730,12 @@ int esacb200_score_poses(esacb200_ctx* ctx, const float* coords, int E, int H, i
     ctx->last_backward = false;
     finish_stats(ctx);
     return ESACB200_OK;
-}
+} ESAC_ABI_CATCH(ctx)
 
 // -------------------------------------------------------------------------------------------------
 int esacb200_refine_poses(esacb200_ctx* ctx, const float* coords, int E, int H, int W, const int64_t* assign,
                           int64_t assign_stride, int M, double* poses6, int shiftX, int shiftY, float f, float ppx,
-                          float ppy, float tau, float maxReproj, int sub, int* out_rounds, int* out_inliers) {
+                          float ppy, float tau, float maxReproj, int sub, int* out_rounds, int* out_inliers) try {
     if (!ctx) return ESACB200_ERR_ARG;
     if (!coords || !assign || !poses6) return fail(ctx, ESACB200_ERR_ARG, "null pointer argument");
     Plan pl;
@@ -768,7 +781,7 @@ int esacb200_refine_poses(esacb200_ctx* ctx, const float* coords, int E, int H, 
     ctx->last_M = M;
     finish_stats(ctx);
     return ESACB200_OK;
-}
+} ESAC_ABI_CATCH(ctx)
 
 
 // -------------------------------------------------------------------------------------------------
@@ -902,19 +915,19 @@ static int backward_impl(esacb200_ctx* ctx, const float* coords, float* grads, i
 int esacb200_backward(esacb200_ctx* ctx, const float* coords, float* grads, int E, int H, int W, const int64_t* assign,
                       int64_t assign_stride, int M, const float* gt_pose, float wRot, float wTrans, float cut, int shiftX,
                       int shiftY, float f, float ppx, float ppy, float tau, float alpha, float beta, float maxReproj, int sub,
-                      double* out_loss) {
+                      double* out_loss) try {
     return backward_impl(ctx, coords, grads, E, H, W, assign, assign_stride, M, gt_pose, wRot, wTrans, cut, shiftX, shiftY, f, ppx,
                          ppy, tau, alpha, beta, maxReproj, sub, nullptr, nullptr, out_loss);
-}
+} ESAC_ABI_CATCH(ctx)
 
 int esacb200_backward_sharded(esacb200_ctx* ctx, const float* coords, float* grads, int E, int H, int W, const int64_t* assign,
                               int64_t assign_stride, int M, const float* gt_pose, float wRot, float wTrans, float cut,
                               int shiftX, int shiftY, float f, float ppx, float ppy, float tau, float alpha, float beta,
-                              float maxReproj, int sub, esacb200_exchange_fn exchange, void* user, double* out_loss) {
+                              float maxReproj, int sub, esacb200_exchange_fn exchange, void* user, double* out_loss) try {
     if (!exchange) return ctx ? fail(ctx, ESACB200_ERR_ARG, "exchange callback is null") : ESACB200_ERR_ARG;
     return backward_impl(ctx, coords, grads, E, H, W, assign, assign_stride, M, gt_pose, wRot, wTrans, cut, shiftX, shiftY, f, ppx,
                          ppy, tau, alpha, beta, maxReproj, sub, exchange, user, out_loss);
-}
+} ESAC_ABI_CATCH(ctx)
 
 // -------------------------------------------------------------------------------------------------
 // esac_backward over a batch.  Every image is an independent problem ("images in a batch are fully
@@ -923,7 +936,7 @@ int esacb200_backward_sharded(esacb200_ctx* ctx, const float* coords, float* gra
 int esacb200_backward_batch(esacb200_ctx* ctx, int B, const float* coords, float* grads, int E, int H, int W,
                             const int64_t* assign, int64_t assign_stride, int M, const float* gt_poses, float wRot,
                             float wTrans, float cut, const int* shiftX, const int* shiftY, float f, float ppx, float ppy,
-                            float tau, float alpha, float beta, float maxReproj, int sub, double* out_losses) {
+                            float tau, float alpha, float beta, float maxReproj, int sub, double* out_losses) try {
     if (!ctx) return ESACB200_ERR_ARG;
     if (!coords || !grads || !assign || !gt_poses || B <= 0) return fail(ctx, ESACB200_ERR_ARG, "null pointer argument or empty batch");
     if (ctx->inj_M) return fail(ctx, ESACB200_ERR_ARG, "injected cells are a single-image test hook");
@@ -953,6 +966,7 @@ int esacb200_backward_batch(esacb200_ctx* ctx, int B, const float* coords, float
     std::vector<esacb200_stats> last((size_t)nw);
     std::vector<unsigned long long> launches((size_t)nw, 0);
     auto work = [&](int wi) {
+        try {
         esacb200_ctx* w = ctx->workers[wi];
         cudaSetDevice(ctx->device);
         w->max_tries = ctx->max_tries;
@@ -974,6 +988,11 @@ int esacb200_backward_batch(esacb200_ctx* ctx, int B, const float* coords, float
             launches[wi] += w->st.kernel_launches;
         }
         last[wi] = w->st;
+        } catch (...) {  // an exception escaping a std::thread would terminate the process
+            rcs[wi] = ESACB200_ERR_ARG;
+            failed_at[wi] = -1;
+            snprintf(ctx->workers[wi]->err, sizeof(ctx->workers[wi]->err), "host-side failure in a batch worker");
+        }
     };
     const auto t0 = std::chrono::steady_clock::now();
     if (nw == 1) {
@@ -995,11 +1014,11 @@ int esacb200_backward_batch(esacb200_ctx* ctx, int B, const float* coords, float
     ctx->last_M = 0;  // the per-hypothesis buffers live in the workers
     ctx->last_backward = true;
     return ESACB200_OK;
-}
+} ESAC_ABI_CATCH(ctx)
 
 // -------------------------------------------------------------------------------------------------
 int esacb200_assign_hypotheses(esacb200_ctx* ctx, int B, int E, int M, const float* weights, int keep_top, int single_expert,
-                               uint64_t seed, int64_t* out_assign, float* out_hist) {
+                               uint64_t seed, int64_t* out_assign, float* out_hist) try {
     if (!ctx) return ESACB200_ERR_ARG;
     if (!weights || !out_assign) return fail(ctx, ESACB200_ERR_ARG, "null pointer argument");
     if (B <= 0 || E <= 0 || M <= 0) return fail(ctx, ESACB200_ERR_ARG, "bad sizes B=%d E=%d M=%d", B, E, M);
@@ -1029,12 +1048,12 @@ int esacb200_assign_hypotheses(esacb200_ctx* ctx, int B, int E, int M, const flo
     if (flags & 1) return fail(ctx, ESACB200_ERR_ARG, "probability tensor contains either inf, nan or element < 0");
     if (flags & 2) return fail(ctx, ESACB200_ERR_ARG, "invalid multinomial distribution (sum of probabilities <= 0)");
     return ESACB200_OK;
-}
+} ESAC_ABI_CATCH(ctx)
 
 // -------------------------------------------------------------------------------------------------
 int esacb200_reproj_loss(esacb200_ctx* ctx, int B, const float* coords, float* grads, int H, int W, const float* gt_poses,
                          const int* shiftX, const int* shiftY, float f, float ppx, float ppy, int sub, float cut,
-                         float maxReproj, float minDepth, double* out_losses) {
+                         float maxReproj, float minDepth, double* out_losses) try {
     if (!ctx) return ESACB200_ERR_ARG;
     if (!coords || !gt_poses || !out_losses) return fail(ctx, ESACB200_ERR_ARG, "null pointer argument");
     if (B <= 0 || H <= 0 || W <= 0 || sub <= 0) return fail(ctx, ESACB200_ERR_ARG, "bad sizes B=%d H=%d W=%d sub=%d", B, H, W, sub);
@@ -1105,16 +1124,16 @@ int esacb200_reproj_loss(esacb200_ctx* ctx, int B, const float* coords, float* g
     ctx->last_M = 0;
     finish_stats(ctx);
     return ESACB200_OK;
-}
+} ESAC_ABI_CATCH(ctx)
 
-int esacb200_copy_last_scores(esacb200_ctx* ctx, double* dst, int M) {
+int esacb200_copy_last_scores(esacb200_ctx* ctx, double* dst, int M) try {
     if (!ctx || !dst) return ESACB200_ERR_ARG;
     if (M != ctx->last_M) return fail(ctx, ESACB200_ERR_ARG, "last call had M=%d, asked for %d", ctx->last_M, M);
     cudaSetDevice(ctx->device);
     CK(cudaMemcpyAsync(dst, ctx->scores.p, (size_t)M * 8, cudaMemcpyDefault, ctx->stream));
     if (!is_device_ptr(dst)) CK(cudaStreamSynchronize(ctx->stream));
     return ESACB200_OK;
-}
+} ESAC_ABI_CATCH(ctx)
 
 int esacb200_get_stats(esacb200_ctx* ctx, esacb200_stats* out) {
     if (!ctx || !out) return ESACB200_ERR_ARG;
@@ -1123,7 +1142,7 @@ int esacb200_get_stats(esacb200_ctx* ctx, esacb200_stats* out) {
 }
 
 int esacb200_get_hypotheses(esacb200_ctx* ctx, double* poses6, int32_t* cells, int32_t* tries, double* scores,
-                            double* probs, double* refined6, double* losses) {
+                            double* probs, double* refined6, double* losses) try {
     if (!ctx) return ESACB200_ERR_ARG;
     const int M = ctx->last_M;
     if (M <= 0) return fail(ctx, ESACB200_ERR_ARG, "no previous call");
@@ -1139,7 +1158,7 @@ int esacb200_get_hypotheses(esacb200_ctx* ctx, double* poses6, int32_t* cells, i
         CK(cudaMemcpy(losses, ctx->losses.p, (size_t)M * 8, cudaMemcpyDeviceToHost));
     }
     return ESACB200_OK;
-}
+} ESAC_ABI_CATCH(ctx)
 
 // ------------------------------------------------------------------------------------------------
 // host test hooks (esac_b200_testhooks.h)
