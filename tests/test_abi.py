@@ -39,6 +39,16 @@ def test_no_cpu_fallback_without_device(lib):
     sc = make_scene(E=1, H=8, W=10, M=4)
     with pytest.raises(RuntimeError, match="no CPU path"):
         api.forward(sc.coords, sc.assign, np.zeros((4, 4), np.float32), *sc.params)
+    # the additive entry points fail the same way: nothing in the product computes on the CPU
+    with pytest.raises(RuntimeError, match="no CPU path"):
+        api.backward(sc.coords, np.zeros_like(sc.coords), sc.assign, sc.gt_pose, 1.0, 100.0, 100.0, *sc.params)
+    with pytest.raises(RuntimeError, match="no CPU path"):
+        api.assign_hypotheses(np.ones((1, 3), np.float32), 8, 1)
+    with pytest.raises(RuntimeError, match="no CPU path"):
+        api.reproj_loss(sc.coords[:1], sc.gt_pose[None], 525.0, 0, 0, 10.0)
+    with pytest.raises(RuntimeError, match="no CPU path"):
+        api.backward_batch(sc.coords[None], np.zeros_like(sc.coords)[None], sc.assign[None], sc.gt_pose[None], 1.0, 100.0, 100.0,
+                           0, 0, *sc.params[2:])
 
 
 def test_argument_checks_mirror_accessor_errors():
