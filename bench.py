@@ -345,6 +345,23 @@ def main():
             line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": workers, "kind": "port",
                                     "sample": f"{take} of {M_local} hypotheses, one full esac.forward "
                                               f"(sample+score+select+refine) via the cv2 oracle, {secs:.1f} s"}
+            # informative: the scoring stage alone in compiled C/OpenMP (oracle/esac_oracle_c.c, no OpenCV, no Python in the
+            # loop) -- an upper bound on what a compiled CPU forward could reach on this host, next to the cv2 port above
+            try:
+                from oracle.build import c_score
+                esac.forward(d_coords[0], d_assign[0], d_out, *params)
+                poses = ctx.hypotheses()["poses"]
+                n_c = min(M_local, max(256, 4 * cores))
+                idx_c = np.linspace(0, M_local - 1, n_c).astype(int)
+                c_score(sc.coords, sc.assign[idx_c[:cores]], poses[idx_c[:cores]], *params)      # warm-up, builds the library
+                t0 = time.perf_counter()
+                _, used = c_score(sc.coords, sc.assign[idx_c], poses[idx_c], *params)
+                dtc = time.perf_counter() - t0
+                line["cpu_baseline"]["compiled_scoring_only"] = {
+                    "value": n_c / dtc, "unit": UNIT, "cores": int(used),
+                    "sample": f"{n_c} of {M_local} hypotheses, getReproErrs+getHypScores restated in C/OpenMP, {dtc:.1f} s"}
+            except Exception as exc:  # never let the informative leg break the bench line
+                line["cpu_baseline"]["compiled_scoring_only"] = {"error": str(exc)[:200]}
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
