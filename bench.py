@@ -172,7 +172,7 @@ def main():
         raise SystemExit("bench.py needs a CUDA device: this implementation has no CPU path")
     torch.cuda.set_device(local_rank)
     if world > 1:
-        os.environ["NCCL_DEBUG"] = "WARN"  # keep NCCL's version banner off stdout: rank 0 prints exactly one JSON line
+        os.environ.setdefault("NCCL_DEBUG", "WARN")  # the driver's own setting (it greps NCCL's communicator lines) wins
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     import esac
@@ -323,7 +323,7 @@ def main():
                 "e2e": {"value": e2e, "unit": UNIT, "ms_per_step": ms_e2e / args.steps,
                         "h2d_bytes_per_step": int(scenes[0].coords.nbytes + scenes[0].assign.nbytes), "d2h_bytes_per_step": 68},
                 "gpu_launches": int(launches), "batched_e2e": batched, "backward": bwd,
-                "roofline": {"kernel": "esacb200::score_kernel<8>", "bound": "hbm", "achieved": achieved, "peak": peak,
+                "roofline": {"kernel": "esacb200::score_kernel_tma<8>", "bound": "hbm", "achieved": achieved, "peak": peak,
                              "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
                              "algorithmic_bytes_per_launch": alg_bytes, "ms_per_launch": t_score * 1e3,
                              "hyps_per_s_kernel_only": M_local / t_score if t_score > 0 else None,

@@ -3,7 +3,9 @@
 The reference's trainer calls the extension, then builds the gating gradient by hand and feeds both gradients to
 torch.autograd.backward (train_esac.py:151-180).  EsacLoss packages exactly that: its forward returns the expected
 pose loss, its backward hands d loss / d sceneCoordinates (from the extension) and the REINFORCE-style gating
-gradient loss * histogram(e_hyps) (train_esac.py:171-176) to autograd.  CUDA tensors stay on the device."""
+gradient to autograd -- loss * histogram(e_hyps) in the default mode (train_esac.py:174-176), or, in the trainer's
+`expertselection` mode (one expert drawn and expanded to all hypotheses, train_esac.py:133-135), `loss` at the drawn
+expert only (train_esac.py:171-173).  CUDA tensors stay on the device."""
 from __future__ import annotations
 
 import torch
@@ -15,26 +17,36 @@ class EsacLoss(torch.autograd.Function):
     @staticmethod
     def forward(ctx, scene_coordinates, gating_log_probs, hyp_assignment, gt_pose, w_rot, w_trans, loss_cut, shift_x,
                 shift_y, focal_length, ppoint_x, ppoint_y, inlier_threshold, inlier_alpha, inlier_beta, max_reproj,
-                sub_sampling):
+                sub_sampling, expert_selection=None):
         grads = torch.zeros_like(scene_coordinates)
         loss = api.backward(scene_coordinates.detach(), grads, hyp_assignment, gt_pose, w_rot, w_trans, loss_cut, shift_x,
                             shift_y, focal_length, ppoint_x, ppoint_y, inlier_threshold, inlier_alpha, inlier_beta,
                             max_reproj, sub_sampling)
         E = scene_coordinates.shape[0]
-        hist = torch.histc(hyp_assignment.float().cpu(), bins=E, min=0, max=E - 1)  # train_esac.py:141
-        ctx.save_for_backward(grads, (loss * hist).to(gating_log_probs.device).reshape(gating_log_probs.shape))
+        if expert_selection is None:
+            # expert.expand(M) (train_esac.py:135-136) is a stride-0 view: that is the expertselection branch
+            expert_selection = hyp_assignment.dim() == 1 and hyp_assignment.shape[0] > 1 and hyp_assignment.stride(0) == 0
+        if expert_selection:
+            g_gating = torch.zeros(E)
+            g_gating[int(hyp_assignment[0])] = loss                                      # train_esac.py:171-173
+        else:
+            hist = torch.histc(hyp_assignment.float().cpu(), bins=E, min=0, max=E - 1)   # train_esac.py:140
+            g_gating = loss * hist                                                        # train_esac.py:174-176
+        ctx.save_for_backward(grads, g_gating.to(gating_log_probs.device).reshape(gating_log_probs.shape))
         return scene_coordinates.new_tensor(loss)
 
     @staticmethod
     def backward(ctx, grad_out):
         g_coords, g_gating = ctx.saved_tensors
-        return (g_coords * grad_out, g_gating * grad_out) + (None,) * 15
+        return (g_coords * grad_out, g_gating * grad_out) + (None,) * 16
 
 
-def esac_loss(scene_coordinates, gating_log_probs, hyp_assignment, gt_pose, *params):
+def esac_loss(scene_coordinates, gating_log_probs, hyp_assignment, gt_pose, *params, expert_selection=None):
     """params: wLossRot, wLossTrans, lossCut, shiftX, shiftY, focalLength, ppointX, ppointY, inlierThreshold,
-    inlierAlpha, inlierBeta, maxReproj, subSampling -- the positional tail of esac.backward."""
-    return EsacLoss.apply(scene_coordinates, gating_log_probs, hyp_assignment, gt_pose, *params)
+    inlierAlpha, inlierBeta, maxReproj, subSampling -- the positional tail of esac.backward.
+    expert_selection: True = the trainer's `expertselection` gating gradient (loss at the drawn expert), False = loss *
+    histogram, None = decide from the assignment tensor (a stride-0 `expert.expand(M)` view means expert selection)."""
+    return EsacLoss.apply(scene_coordinates, gating_log_probs, hyp_assignment, gt_pose, *params, expert_selection)
 
 
 class ReprojLoss(torch.autograd.Function):

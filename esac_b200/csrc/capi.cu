@@ -92,6 +92,21 @@ struct esacb200_ctx {
 
 namespace {
 
+// Every entry point works on the context's device and leaves the caller's current device as it found it (torch reads the
+// current device with cudaGetDevice: a library that silently switches it redirects the caller's later allocations).
+struct DeviceGuard {
+    int prev = -1;
+    explicit DeviceGuard(int device) {
+        if (cudaGetDevice(&prev) != cudaSuccess) { cudaGetLastError(); prev = -1; }
+        if (prev != device) cudaSetDevice(device);
+    }
+    ~DeviceGuard() {
+        if (prev >= 0) cudaSetDevice(prev);
+    }
+    DeviceGuard(const DeviceGuard&) = delete;
+    DeviceGuard& operator=(const DeviceGuard&) = delete;
+};
+
 int fail(esacb200_ctx* c, int code, const char* fmt, ...) {
     va_list ap;
     va_start(ap, fmt);
@@ -413,7 +428,6 @@ void begin_call(esacb200_ctx* ctx) {
     memset(&ctx->st, 0, sizeof(ctx->st));
     for (int i = 0; i < EV_COUNT; ++i) ctx->ev_used[i] = false;
     ctx->err[0] = 0;
-    cudaSetDevice(ctx->device);
     mark(ctx, EV_START);
 }
 
@@ -456,6 +470,7 @@ int esacb200_create(int device, esacb200_ctx** out) {
     esacb200_ctx* ctx = new (std::nothrow) esacb200_ctx();
     if (!ctx) return ESACB200_ERR_ARG;
     ctx->device = device;
+    DeviceGuard device_guard(device);
     if (cudaSetDevice(device) != cudaSuccess) { delete ctx; return ESACB200_ERR_NO_DEVICE; }
     cudaDeviceProp prop;
     if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) { delete ctx; return ESACB200_ERR_CUDA; }
@@ -489,7 +504,7 @@ void esacb200_destroy(esacb200_ctx* ctx) {
     if (!ctx) return;
     for (esacb200_ctx* w : ctx->workers) esacb200_destroy(w);
     ctx->workers.clear();
-    cudaSetDevice(ctx->device);
+    DeviceGuard device_guard(ctx->device);
     cudaStreamSynchronize(ctx->stream);
     DevBuf* bufs[] = {&ctx->coords, &ctx->grads, &ctx->assign64, &ctx->assign32, &ctx->counts, &ctx->offsets, &ctx->perm,
                       &ctx->slot_of, &ctx->chunks, &ctx->scalars, &ctx->centres, &ctx->poses, &ctx->poses_ref, &ctx->cells,
@@ -547,7 +562,7 @@ int esacb200_set_option(esacb200_ctx* ctx, const char* key, double v) {
 
 int esacb200_inject_cells(esacb200_ctx* ctx, const int32_t* cells, int M, int T) try {
     if (!ctx) return ESACB200_ERR_ARG;
-    cudaSetDevice(ctx->device);
+    DeviceGuard device_guard(ctx->device);
     if (!cells) { ctx->inj_M = ctx->inj_T = 0; return ESACB200_OK; }
     if (M <= 0 || T <= 0) return fail(ctx, ESACB200_ERR_ARG, "inject_cells: M and T must be positive");
     size_t bytes = (size_t)M * T * 8 * 4;
@@ -570,6 +585,7 @@ int esacb200_forward(esacb200_ctx* ctx, const float* coords, int E, int H, int W
                      int64_t assign_stride, int M, float* out_pose, int shiftX, int shiftY, float f, float ppx,
                      float ppy, float tau, float alpha, float beta, float maxReproj, int sub, int* out_expert) try {
     if (!ctx) return ESACB200_ERR_ARG;
+    DeviceGuard device_guard(ctx->device);
     if (!coords || !assign || !out_pose) return fail(ctx, ESACB200_ERR_ARG, "null pointer argument");
     Plan pl;
     int rc = fill_problem(ctx, pl.P, E, H, W, M, shiftX, shiftY, f, ppx, ppy, tau, alpha, beta, maxReproj, sub);
@@ -612,6 +628,7 @@ int esacb200_forward_pack(esacb200_ctx* ctx, const float* coords, int E, int H, 
                           int64_t assign_stride, int M, int shiftX, int shiftY, float f, float ppx, float ppy, float tau,
                           float alpha, float beta, float maxReproj, int sub, int expert_offset, double* pack_out) try {
     if (!ctx) return ESACB200_ERR_ARG;
+    DeviceGuard device_guard(ctx->device);
     if (!coords || !assign || !pack_out) return fail(ctx, ESACB200_ERR_ARG, "null pointer argument");
     if (!is_device_ptr(coords) || !is_device_ptr(assign) || !is_device_ptr(pack_out))
         return fail(ctx, ESACB200_ERR_ARG, "forward_pack takes device pointers only");
@@ -644,6 +661,7 @@ int esacb200_forward_batch(esacb200_ctx* ctx, int B, const float* coords, int E,
                            int64_t assign_stride, int M, float* out_poses, int shiftX, int shiftY, float f, float ppx,
                            float ppy, float tau, float alpha, float beta, float maxReproj, int sub, int* out_experts) try {
     if (!ctx) return ESACB200_ERR_ARG;
+    DeviceGuard device_guard(ctx->device);
     if (!coords || !assign || !out_poses || B <= 0) return fail(ctx, ESACB200_ERR_ARG, "null pointer argument or empty batch");
     Plan pl;
     int rc = fill_problem(ctx, pl.P, E, H, W, M, shiftX, shiftY, f, ppx, ppy, tau, alpha, beta, maxReproj, sub);
@@ -705,6 +723,7 @@ int esacb200_score_poses(esacb200_ctx* ctx, const float* coords, int E, int H, i
                          int64_t assign_stride, int M, const double* poses6, int shiftX, int shiftY, float f, float ppx,
                          float ppy, float tau, float alpha, float beta, float maxReproj, int sub, double* out_scores) try {
     if (!ctx) return ESACB200_ERR_ARG;
+    DeviceGuard device_guard(ctx->device);
     if (!coords || !assign || !poses6 || !out_scores) return fail(ctx, ESACB200_ERR_ARG, "null pointer argument");
     Plan pl;
     int rc = fill_problem(ctx, pl.P, E, H, W, M, shiftX, shiftY, f, ppx, ppy, tau, alpha, beta, maxReproj, sub);
@@ -737,6 +756,7 @@ int esacb200_refine_poses(esacb200_ctx* ctx, const float* coords, int E, int H, 
                           int64_t assign_stride, int M, double* poses6, int shiftX, int shiftY, float f, float ppx,
                           float ppy, float tau, float maxReproj, int sub, int* out_rounds, int* out_inliers) try {
     if (!ctx) return ESACB200_ERR_ARG;
+    DeviceGuard device_guard(ctx->device);
     if (!coords || !assign || !poses6) return fail(ctx, ESACB200_ERR_ARG, "null pointer argument");
     Plan pl;
     int rc = fill_problem(ctx, pl.P, E, H, W, M, shiftX, shiftY, f, ppx, ppy, tau, 100.f, 0.5f, maxReproj, sub);
@@ -790,6 +810,7 @@ static int backward_impl(esacb200_ctx* ctx, const float* coords, float* grads, i
                          int shiftY, float f, float ppx, float ppy, float tau, float alpha, float beta, float maxReproj, int sub,
                          esacb200_exchange_fn exchange, void* user, double* out_loss) {
     if (!ctx) return ESACB200_ERR_ARG;
+    DeviceGuard device_guard(ctx->device);
     if (!coords || !assign || !grads || !gt_pose) return fail(ctx, ESACB200_ERR_ARG, "null pointer argument");
     Plan pl;
     int rc = fill_problem(ctx, pl.P, E, H, W, M, shiftX, shiftY, f, ppx, ppy, tau, alpha, beta, maxReproj, sub);
@@ -938,10 +959,10 @@ int esacb200_backward_batch(esacb200_ctx* ctx, int B, const float* coords, float
                             float wTrans, float cut, const int* shiftX, const int* shiftY, float f, float ppx, float ppy,
                             float tau, float alpha, float beta, float maxReproj, int sub, double* out_losses) try {
     if (!ctx) return ESACB200_ERR_ARG;
+    DeviceGuard device_guard(ctx->device);
     if (!coords || !grads || !assign || !gt_poses || B <= 0) return fail(ctx, ESACB200_ERR_ARG, "null pointer argument or empty batch");
     if (ctx->inj_M) return fail(ctx, ESACB200_ERR_ARG, "injected cells are a single-image test hook");
     if (E <= 0 || H <= 0 || W <= 0 || M <= 0) return fail(ctx, ESACB200_ERR_ARG, "bad sizes E=%d H=%d W=%d M=%d", E, H, W, M);
-    cudaSetDevice(ctx->device);
     const size_t cstride = (size_t)E * 3 * H * W;
     const int64_t arow = assign_stride == 0 ? 0 : (int64_t)M * assign_stride;
     std::vector<float> gt_host;
@@ -1020,10 +1041,10 @@ int esacb200_backward_batch(esacb200_ctx* ctx, int B, const float* coords, float
 int esacb200_assign_hypotheses(esacb200_ctx* ctx, int B, int E, int M, const float* weights, int keep_top, int single_expert,
                                uint64_t seed, int64_t* out_assign, float* out_hist) try {
     if (!ctx) return ESACB200_ERR_ARG;
+    DeviceGuard device_guard(ctx->device);
     if (!weights || !out_assign) return fail(ctx, ESACB200_ERR_ARG, "null pointer argument");
     if (B <= 0 || E <= 0 || M <= 0) return fail(ctx, ESACB200_ERR_ARG, "bad sizes B=%d E=%d M=%d", B, E, M);
     if (E > assign_max_experts()) return fail(ctx, ESACB200_ERR_ARG, "E=%d exceeds the %d experts one CTA holds", E, assign_max_experts());
-    cudaSetDevice(ctx->device);
     const bool w_host = !is_device_ptr(weights), a_host = !is_device_ptr(out_assign), h_host = out_hist && !is_device_ptr(out_hist);
     const size_t wb = (size_t)B * E * sizeof(float), ab = (size_t)B * M * sizeof(int64_t);
     // staging layout in `scratch`: [flags int (16 B)] [weights] [hist] [assign]
@@ -1055,10 +1076,10 @@ int esacb200_reproj_loss(esacb200_ctx* ctx, int B, const float* coords, float* g
                          const int* shiftX, const int* shiftY, float f, float ppx, float ppy, int sub, float cut,
                          float maxReproj, float minDepth, double* out_losses) try {
     if (!ctx) return ESACB200_ERR_ARG;
+    DeviceGuard device_guard(ctx->device);
     if (!coords || !gt_poses || !out_losses) return fail(ctx, ESACB200_ERR_ARG, "null pointer argument");
     if (B <= 0 || H <= 0 || W <= 0 || sub <= 0) return fail(ctx, ESACB200_ERR_ARG, "bad sizes B=%d H=%d W=%d sub=%d", B, H, W, sub);
     if ((long long)H * W > (1ll << 30)) return fail(ctx, ESACB200_ERR_ARG, "map %dx%d too large", W, H);
-    cudaSetDevice(ctx->device);
     begin_call(ctx);
     const int N = H * W;
     const size_t cbytes = (size_t)B * 3 * N * sizeof(float);
@@ -1128,8 +1149,8 @@ int esacb200_reproj_loss(esacb200_ctx* ctx, int B, const float* coords, float* g
 
 int esacb200_copy_last_scores(esacb200_ctx* ctx, double* dst, int M) try {
     if (!ctx || !dst) return ESACB200_ERR_ARG;
+    DeviceGuard device_guard(ctx->device);
     if (M != ctx->last_M) return fail(ctx, ESACB200_ERR_ARG, "last call had M=%d, asked for %d", ctx->last_M, M);
-    cudaSetDevice(ctx->device);
     CK(cudaMemcpyAsync(dst, ctx->scores.p, (size_t)M * 8, cudaMemcpyDefault, ctx->stream));
     if (!is_device_ptr(dst)) CK(cudaStreamSynchronize(ctx->stream));
     return ESACB200_OK;
@@ -1144,9 +1165,9 @@ int esacb200_get_stats(esacb200_ctx* ctx, esacb200_stats* out) {
 int esacb200_get_hypotheses(esacb200_ctx* ctx, double* poses6, int32_t* cells, int32_t* tries, double* scores,
                             double* probs, double* refined6, double* losses) try {
     if (!ctx) return ESACB200_ERR_ARG;
+    DeviceGuard device_guard(ctx->device);
     const int M = ctx->last_M;
     if (M <= 0) return fail(ctx, ESACB200_ERR_ARG, "no previous call");
-    cudaSetDevice(ctx->device);
     if (poses6) CK(cudaMemcpy(poses6, ctx->poses.p, (size_t)M * sizeof(Pose), cudaMemcpyDeviceToHost));
     if (cells) CK(cudaMemcpy(cells, ctx->cells.p, (size_t)M * 32, cudaMemcpyDeviceToHost));
     if (tries) CK(cudaMemcpy(tries, ctx->tries.p, (size_t)M * 4, cudaMemcpyDeviceToHost));

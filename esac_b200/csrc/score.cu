@@ -13,6 +13,8 @@
 //   err = |p| / |z|,  p = (xc + (cx-px) z, yc + (cy-py) z)   ->  err = num * rsqrt(num * z^2)
 //   w   = 1 / (1 + 2^(k1*min(err,maxReproj) + k0))           ==  1 - sigmoid(beta*(err - tau))
 // i.e. 3 MUFU (rsq, ex2, rcp) and ~20 fp32-pipe ops issued as FFMA2/FMUL2/FADD2.
+#include <atomic>
+
 #include "esac_internal.h"
 
 namespace esacb200 {
@@ -437,17 +439,25 @@ __global__ void __launch_bounds__(kScoreThreads, 2) score_kernel_tma(const __gri
 
 int score_tile_pixels(int ppt) { return kScoreThreads * ppt; }
 
+constexpr int kMaxDevices = 64;
+
 void launch_score(const ScoreArgs& a, int ppt, int grid, cudaStream_t st) {
     if (a.vec_ok && ppt >= 4) {  // TMA path (bulk copies need 16-byte granularity)
         const size_t smem = (size_t)2 * 3 * kScoreThreads * ppt * sizeof(float);
-        static bool attr_set[2] = {false, false};
-        if (ppt == 8) {
-            if (!attr_set[0]) { cudaFuncSetAttribute(score_kernel_tma<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); attr_set[0] = true; }
-            score_kernel_tma<8><<<grid, kScoreThreads, smem, st>>>(a);
-        } else {
-            if (!attr_set[1]) { cudaFuncSetAttribute(score_kernel_tma<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); attr_set[1] = true; }
-            score_kernel_tma<4><<<grid, kScoreThreads, smem, st>>>(a);
+        // The opt-in above 48 KB of dynamic shared memory is a per-DEVICE function attribute (one process may hold contexts
+        // on several GPUs, api.context(device)), and launches may come from several host threads (backward_batch workers).
+        static std::atomic<unsigned char> attr_set[kMaxDevices][2];
+        int dev = 0;
+        cudaGetDevice(&dev);
+        const int which = ppt == 8 ? 0 : 1;
+        const bool known = dev >= 0 && dev < kMaxDevices;
+        if (!known || !attr_set[dev][which].load(std::memory_order_acquire)) {
+            if (ppt == 8) cudaFuncSetAttribute(score_kernel_tma<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            else cudaFuncSetAttribute(score_kernel_tma<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            if (known) attr_set[dev][which].store(1, std::memory_order_release);
         }
+        if (ppt == 8) score_kernel_tma<8><<<grid, kScoreThreads, smem, st>>>(a);
+        else score_kernel_tma<4><<<grid, kScoreThreads, smem, st>>>(a);
         return;
     }
     if (ppt == 8) score_kernel<8><<<grid, kScoreThreads, 0, st>>>(a);

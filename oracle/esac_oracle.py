@@ -22,18 +22,21 @@ including the float/double mix, the x-outer/y-inner point order, EPS / PROB_THRE
 the ``> 10`` clamps, the dLoss cut quirk, ``PI`` vs ``CV_PI`` and the ``irand`` off-by-one
 (last row / column never sampled).
 
-PARITY UNPINNED (stated per the task contract): the reference ships no tests, golden vectors or
-fixtures and cannot be compiled here (needs OpenCV C++ headers/libs, which
-this image lacks), so this restatement is not pinned against outputs of the compiled reference.
-What *is* real: every geometric primitive is executed by OpenCV itself (4.13, the reference
-names 3.4.2), and the restatement is cross-checked by known-answer tests (exact pose recovery)
-and finite differences of an fp64 restatement (tests/test_oracle.py).
+PARITY PINNED against the reference's own compiled code: oracle/_ref/esac_ref is the unmodified
+/root/reference/code/esac/{esac.cpp, thread_rand.cpp} + headers, compiled by oracle/build_ref.py against a minimal
+<opencv2/opencv.hpp> stand-in whose solvePnP / projectPoints / Rodrigues / Mat::inv are executed by the real OpenCV of the
+cv2 wheel.  Run single-threaded on its default std::mt19937 stream (reproduced here by ThreadRandStream) it returns the
+same winning expert, a bit-identical pose, the same expected loss (<= 5e-11) and the same gradients (<= 3e-9 relative)
+as this file on every case of tests/test_ref_pin.py and tests/golden/make_ref_golden.py, including 480x640 and
+world-scale maps; its outputs are committed as tests/golden/ref_*.npz.  What remains unpinned: OpenCV 4.13 (the wheel)
+instead of the 3.4.2 the reference's README names -- no 3.4.2 binary exists in this image.
 
 One deliberate, documented deviation: the reference draws minimal sets from per-OpenMP-thread
 ``std::mt19937`` streams (thread_rand.cpp:13-30) whose consumption order depends on the OpenMP
-schedule and which Python cannot reseed -- its sample stream is not reproducible even against
-itself.  The oracle therefore uses the counter-based generator ``cell_draw`` below (shared,
-bit for bit, with the CUDA path), or explicit minimal-set injection (``injected_cells``).  The
+schedule -- with more than one thread its sample stream is not reproducible even against itself.
+Besides the single-thread stream (``mt=ThreadRandStream()``, used for the pin) the oracle therefore
+offers the counter-based generator ``cell_draw`` below (shared, bit for bit, with the CUDA path)
+and explicit minimal-set injection (``injected_cells``).  The
 *distribution* is the reference's: x in [0, W-2], y in [0, H-2], 4 distinct cells, retry until
 the 4-point reprojection gate passes.
 """
@@ -92,6 +95,57 @@ def draw_minimal_set(seed: int, h: int, t: int, W: int, H: int) -> list[tuple[in
         if c in cells:
             continue
         cells.append(c)
+    return cells
+
+
+# --------------------------------------------------------------------------------------
+# the reference's own stream (thread_rand.cpp:7-71) for ONE OpenMP thread
+# --------------------------------------------------------------------------------------
+class ThreadRandStream:
+    """std::mt19937 seeded like ThreadRand::init (thread_rand.cpp:13-30: generator i gets seed + i; default seed 1305)
+    + libstdc++'s std::uniform_int_distribution<int> (GCC >= 11: Lemire's nearly-divisionless reduction of one 32-bit
+    draw, bits/uniform_int_dist.h `_S_nd`).  With OMP_NUM_THREADS=1 the compiled reference consumes exactly this stream,
+    hypothesis after hypothesis, try after try -- which is how tests/test_ref_pin.py runs oracle/_ref and this oracle on
+    identical minimal sets.  The state persists across calls, as the reference's static generators do."""
+
+    def __init__(self, seed: int = 1305, tid: int = 0):
+        self.bg = np.random.MT19937()
+        self.bg._legacy_seeding(int(seed) + int(tid))  # init_genrand(seed) == std::mt19937::seed(seed)
+        self._buf = np.empty(0, np.uint64)
+        self._pos = 0
+        self.draws = 0
+
+    def _next32(self) -> int:
+        if self._pos >= len(self._buf):
+            self._buf = self.bg.random_raw(4096)
+            self._pos = 0
+        v = int(self._buf[self._pos])
+        self._pos += 1
+        self.draws += 1
+        return v
+
+    def irand(self, inc_min: int, exc_max: int) -> int:
+        """irand(incMin, excMax) -> uniform_int_distribution(incMin, excMax - 1) (thread_rand.cpp:68-71)."""
+        rng = (exc_max - 1) - inc_min + 1
+        p = self._next32() * rng
+        low = p & 0xFFFFFFFF
+        if low < rng:
+            thr = ((1 << 32) - rng) % rng
+            while low < thr:
+                p = self._next32() * rng
+                low = p & 0xFFFFFFFF
+        return inc_min + (p >> 32)
+
+
+def draw_minimal_set_mt(mt: ThreadRandStream, W: int, H: int) -> list[tuple[int, int]]:
+    """esac_util.h:164-176 on the reference's own stream: x = irand(0, imW-1), y = irand(0, imH-1), duplicates re-drawn."""
+    cells: list[tuple[int, int]] = []
+    while len(cells) < 4:
+        x = mt.irand(0, W - 1)
+        y = mt.irand(0, H - 1)
+        if (x, y) in cells:
+            continue
+        cells.append((x, y))
     return cells
 
 
@@ -203,9 +257,10 @@ class Hyp:
 # --------------------------------------------------------------------------------------
 # esac_util.h
 # --------------------------------------------------------------------------------------
-def sample_hypotheses(coords, assign, sampling, K, max_tries, tau, seed=1305, injected_cells=None):
+def sample_hypotheses(coords, assign, sampling, K, max_tries, tau, seed=1305, injected_cells=None, mt=None):
     """esac_util.h:129-225.  ``injected_cells``: int array [M, T, 4, 2] of candidate minimal sets
-    (x, y) per hypothesis, tried in order; otherwise the counter stream (seed, h, t)."""
+    (x, y) per hypothesis, tried in order; ``mt``: a ThreadRandStream = the reference's own single-thread stream;
+    otherwise the counter stream (seed, h, t)."""
     E, _, H, W = coords.shape
     hyps = []
     for h in range(len(assign)):
@@ -213,7 +268,9 @@ def sample_hypotheses(coords, assign, sampling, K, max_tries, tau, seed=1305, in
         hyp = Hyp(np.zeros((3, 1)), np.zeros((3, 1)))
         n_tries = max_tries if injected_cells is None else min(max_tries, injected_cells.shape[1])
         for t in range(n_tries):
-            if injected_cells is None:
+            if mt is not None:
+                cells = draw_minimal_set_mt(mt, W, H)
+            elif injected_cells is None:
                 cells = draw_minimal_set(seed, h, t, W, H)
             else:
                 cells = [(int(c[0]), int(c[1])) for c in injected_cells[h, t]]
@@ -551,7 +608,7 @@ class ForwardTrace:
 
 
 def forward(coords, assign, out_pose, shiftX, shiftY, f, ppx, ppy, tau, alpha, beta, max_reproj, sub,
-            seed=1305, injected_cells=None, max_tries=MAX_SAMPLING_TRIES, trace=False):
+            seed=1305, injected_cells=None, max_tries=MAX_SAMPLING_TRIES, trace=False, mt=None):
     """esac.cpp:64-190.  coords f32 [E,3,H,W], assign i64 [M], out_pose f32 [4,4] written in place.
     Returns the winning expert index (and a ForwardTrace when ``trace``)."""
     coords = np.asarray(coords)
@@ -561,7 +618,7 @@ def forward(coords, assign, out_pose, shiftX, shiftY, f, ppx, ppy, tau, alpha, b
     H, W = coords.shape[2], coords.shape[3]
     K = cam_mat(f, ppx, ppy)
     sampling = create_sampling(W, H, sub, shiftX, shiftY)
-    hyps = sample_hypotheses(coords, assign, sampling, K, max_tries, tau, seed, injected_cells)
+    hyps = sample_hypotheses(coords, assign, sampling, K, max_tries, tau, seed, injected_cells, mt)
     errs = [get_repro_errs(coords, hy.rvec, hy.tvec, int(assign[h]), sampling, K, max_reproj)[0]
             for h, hy in enumerate(hyps)]
     scores = get_hyp_scores(errs, tau, alpha, beta)
@@ -590,7 +647,7 @@ class BackwardTrace:
 
 
 def backward(coords, out_grads, assign, gt_pose, w_rot, w_trans, cut, shiftX, shiftY, f, ppx, ppy, tau, alpha,
-             beta, max_reproj, sub, seed=1305, injected_cells=None, max_tries=MAX_SAMPLING_TRIES, trace=False):
+             beta, max_reproj, sub, seed=1305, injected_cells=None, max_tries=MAX_SAMPLING_TRIES, trace=False, mt=None):
     """esac.cpp:213-511.  out_grads f32 [E,3,H,W] is ACCUMULATED in place.  Returns expected loss."""
     coords = np.asarray(coords)
     assert coords.dtype == np.float32 and coords.ndim == 4
@@ -603,7 +660,7 @@ def backward(coords, out_grads, assign, gt_pose, w_rot, w_trans, cut, shiftX, sh
     K = cam_mat(f, ppx, ppy)
     gtT = np.asarray(gt_pose, np.float32).astype(np.float64)
     sampling = create_sampling(W, H, sub, shiftX, shiftY)
-    hyps = sample_hypotheses(coords, assign, sampling, K, max_tries, tau, seed, injected_cells)
+    hyps = sample_hypotheses(coords, assign, sampling, K, max_tries, tau, seed, injected_cells, mt)
     errs, jacs = [], []
     for h, hy in enumerate(hyps):
         e_, j_ = get_repro_errs(coords, hy.rvec, hy.tvec, int(assign[h]), sampling, K, max_reproj, True)

@@ -84,6 +84,32 @@ def test_autograd_wrapper_matches_manual_gradients(api):
     assert np.allclose(gating.grad.cpu().numpy().ravel(), l_ref * hist, rtol=1e-6)
 
 
+def test_autograd_wrapper_expert_selection_branch(api):
+    """train_esac.py:133-136,171-173: one expert drawn and expanded to all hypotheses -> the gating gradient is `loss` at
+    that expert (not loss * M, which the histogram formula of the other branch would give)."""
+    import torch
+    from esac_b200.autograd import esac_loss
+    sc = make_scene(E=3, H=24, W=32, M=24, sub=8, seed=13)
+    expert = torch.tensor([sc.gt_expert], dtype=torch.int64)
+    e_hyps = expert.expand(24)  # stride-0 view, exactly what the trainer builds
+    for flag in (None, True):
+        coords = torch.from_numpy(sc.coords).cuda().requires_grad_(True)
+        gating = torch.log_softmax(torch.zeros(1, 3, device="cuda"), dim=1).requires_grad_(True)
+        api.set_seed(10)
+        loss = esac_loss(coords, gating, e_hyps, torch.from_numpy(sc.gt_pose), 1.0, 100.0, 100.0, *sc.params, expert_selection=flag)
+        loss.backward()
+        want = np.zeros(3, np.float32)
+        want[sc.gt_expert] = loss.item()
+        assert np.allclose(gating.grad.cpu().numpy().ravel(), want, rtol=1e-6)
+    # the same assignment as a materialised tensor with expert_selection=False is the histogram branch
+    coords = torch.from_numpy(sc.coords).cuda().requires_grad_(True)
+    gating = torch.log_softmax(torch.zeros(1, 3, device="cuda"), dim=1).requires_grad_(True)
+    api.set_seed(10)
+    loss = esac_loss(coords, gating, e_hyps.contiguous(), torch.from_numpy(sc.gt_pose), 1.0, 100.0, 100.0, *sc.params)
+    loss.backward()
+    assert np.allclose(gating.grad.cpu().numpy().ravel()[sc.gt_expert], 24 * loss.item(), rtol=1e-6)
+
+
 def test_reference_training_step_runs_through_the_drop_in_module():
     """examples/train_step_synthetic.py = train_esac.py:105-183 with stand-in networks: esac.backward drives autograd."""
     import runpy

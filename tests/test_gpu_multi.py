@@ -87,3 +87,28 @@ def test_two_gpu_sharding_reproduces_single_gpu():
         scale = max(np.abs(ref["ref_grads"]).max(), 1e-12)
         assert np.abs(res[r]["grads"] - ref["ref_grads"][sl]).max() / scale < 1e-6
     assert np.abs(ref["ref_grads"]).max() > 0
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs (gpurun --gpus 2)")
+def test_one_process_two_devices_full_resolution_and_current_device_kept():
+    """One process, contexts on cuda:0 and cuda:1: the scoring kernel's >48 KB shared-memory opt-in is a per-device
+    attribute (it used to be set once per process), and no entry point may leave the caller's current device switched."""
+    import esac_b200.api as api
+    sc = make_scene(E=2, H=480, W=640, M=32, sub=1, seed=3)
+    outs = []
+    torch.cuda.set_device(0)
+    for d in (0, 1):
+        ctx = api.context(d)
+        ctx.set_option("fixed_seed", 1)
+        ctx.set_seed(9)
+        out = torch.zeros(4, 4, device=f"cuda:{d}")
+        e = api.forward(torch.from_numpy(sc.coords).to(f"cuda:{d}"), torch.from_numpy(sc.assign).to(f"cuda:{d}"), out, *sc.params)
+        assert torch.cuda.current_device() == 0          # tensors on cuda:1 did not move the caller's device
+        g = torch.zeros(sc.coords.shape, device=f"cuda:{d}")
+        ctx.set_seed(9)
+        api.backward(torch.from_numpy(sc.coords).to(f"cuda:{d}"), g, torch.from_numpy(sc.assign).to(f"cuda:{d}"),
+                     torch.from_numpy(sc.gt_pose), 1.0, 100.0, 100.0, *sc.params)
+        assert torch.cuda.current_device() == 0
+        outs.append((e, out.cpu().numpy(), g.cpu().numpy()))
+    assert outs[0][0] == outs[1][0]
+    assert np.array_equal(outs[0][1], outs[1][1]) and np.array_equal(outs[0][2], outs[1][2])

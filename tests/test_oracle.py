@@ -84,8 +84,8 @@ def test_backward_accumulates_and_only_touches_assigned_experts():
 
 
 def test_golden_fixtures_still_reproduce():
-    """tests/golden/*.npz were written by tests/golden/make_golden.py from this oracle."""
-    files = sorted(GOLD.glob("*.npz"))
+    """tests/golden/*.npz (other than ref_*) were written by tests/golden/make_golden.py from this oracle."""
+    files = sorted(p for p in GOLD.glob("*.npz") if not p.name.startswith("ref_"))
     assert files, "run python tests/golden/make_golden.py"
     for f in files:
         z = np.load(f)
@@ -209,3 +209,29 @@ def test_reproj_loss_oracle_gradient_matches_closed_form():
             G[:, y, x] = Tinv[:, :3].T @ gc / (H * W)
     assert abs(loss - total / (H * W)) < 1e-12 * max(1.0, abs(loss))
     assert np.abs(g.numpy() - G).max() < 1e-12 * max(1.0, np.abs(G).max())
+
+
+# ---- the oracle against outputs of the reference's own compiled code (tests/golden/ref_*.npz) -------------------------
+def _ref_fixtures_small():
+    from ref_golden_util import REF_GOLD
+    return [p for p in REF_GOLD if "coords" in np.load(p).files]
+
+
+@pytest.mark.parametrize("path", _ref_fixtures_small(), ids=lambda p: p.stem)
+def test_oracle_reproduces_the_compiled_reference_fixtures(path):
+    """No /root/reference needed: the fixtures were written by oracle/_ref (unmodified esac.cpp on the real OpenCV, single
+    thread, default mt19937 stream); ThreadRandStream replays that stream."""
+    from ref_golden_util import params_of
+    z = np.load(path)
+    params = params_of(z)
+    out = np.zeros((4, 4), np.float32)
+    e, tr = O.forward(z["coords"], z["assign"], out, *params, mt=O.ThreadRandStream(1305), trace=True)
+    assert e == int(z["expert"])
+    assert np.abs(out - z["pose"]).max() <= 1e-6
+    assert [h.tries for h in tr.hyps] == z["tries"].tolist()
+    assert [[list(c) for c in h.cells] for h in tr.hyps] == z["cells"][:, -1].tolist()
+    g = np.zeros_like(z["coords"])
+    w_rot, w_trans, cut = (float(v) for v in z["loss_args"])
+    loss = O.backward(z["coords"], g, z["assign"], z["gt_pose"], w_rot, w_trans, cut, *params, mt=O.ThreadRandStream(1305))
+    assert abs(loss - float(z["loss"])) <= 1e-9 * max(1.0, abs(float(z["loss"])))
+    assert np.abs(g - z["grads"]).max() <= 1e-6 * np.abs(z["grads"]).max()
