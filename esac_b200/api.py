@@ -76,6 +76,8 @@ def load_library() -> C.CDLL:
     lib.esacb200_backward_sharded.restype = i32
     lib.esacb200_score_poses.argtypes = [vp, vp, i32, i32, i32, vp, i64, i32, vp] + cam + [vp]
     lib.esacb200_refine_poses.argtypes = [vp, vp, i32, i32, i32, vp, i64, i32, vp, i32, i32, f32, f32, f32, f32, f32, i32, vp, vp]
+    lib.esacb200_get_refine_profile.argtypes = [vp, vp]
+    lib.esacb200_get_refine_profile.restype = i32
     lib.esacb200_get_stats.argtypes = [vp, C.POINTER(Stats)]
     lib.esacb200_get_hypotheses.argtypes = [vp, vp, vp, vp, vp, vp, vp, vp]
     lib.esacb200_device_info.argtypes = [vp, C.POINTER(i32), C.c_char_p, i32]
@@ -167,6 +169,12 @@ class Context:
         s = Stats()
         self.check(self.lib.esacb200_get_stats(self.handle, C.byref(s)))
         return s.as_dict()
+
+    def refine_profile(self) -> np.ndarray:
+        """Phase cycle counters of the last refinement (option "refine_profile" = 1), see include/esac_b200.h."""
+        out = np.zeros(16, np.int64)
+        self.check(self.lib.esacb200_get_refine_profile(self.handle, out.ctypes.data))
+        return out
 
     def copy_last_scores(self, dst):
         """dst: float64 torch tensor (CUDA or CPU) or numpy array of M elements; stream-ordered copy."""

@@ -69,6 +69,8 @@ struct esacb200_ctx {
     int max_ref_steps = 100;
     int fixed_seed = 0;
     int refine_group_opt = 0;
+    int refine_profile = 0;    // 1: block 0 of the refinement kernel records phase cycle counts (esacb200_get_refine_profile)
+    int refine_jobs_per_group = 3;
     int sample_prefilter = 1;
     int hyp_offset = 0;
     int score_ppt_opt = 0, score_hc_opt = 0;
@@ -77,7 +79,7 @@ struct esacb200_ctx {
     // workspace
     DevBuf coords, grads, assign64, assign32, counts, offsets, perm, slot_of, chunks, scalars, centres, poses, poses_ref,
         cells, tries, posepk, part, scores, probs, stats, contrib, masks, rounds, scratch, barrier, out17, inject,
-        losses, red, hypgrad, job_of, gt, smp_int, smp_surv, coords4, coords_alt, assign64_alt, out_batch;
+        losses, red, hypgrad, job_of, gt, smp_int, smp_surv, coords4, coords_alt, assign64_alt, out_batch, prof;
     float* h_out = nullptr;  // pinned staging: 32 floats
     double* h_dbl = nullptr; // pinned staging: 8 doubles
     int inj_M = 0, inj_T = 0;
@@ -356,7 +358,14 @@ int pick_group(esacb200_ctx* ctx, const Problem& P, int jobs_hint) {
     // than the fp64 work it spreads, at every shape measured (profiles/r01m_refine_groups.txt: 60x80 -> 16, 480x640 -> 148)
     int g = words / 10;
     if (g < 1) g = 1;
-    int cap = ctx->refine_coresident / (jobs_hint > 0 ? jobs_hint : 1);
+    // Jobs are handed out dynamically inside the kernel, so a group may work through several jobs: fewer, larger groups even
+    // out the differing job lengths (rounds x LM iterations) -- worth it only while a block's share of the map stays large
+    // against the cost of a group exchange (480x640: 8.5 vs 11.2 ms for 47 jobs; 60x80: 0.79 vs 0.39 ms, so not there;
+    // profiles/r02e_refine_timing.txt)
+    int waves = jobs_hint >= 8 ? ctx->refine_jobs_per_group : 1;
+    int concurrent = jobs_hint > 0 ? (jobs_hint + waves - 1) / waves : 1;
+    int cap = ctx->refine_coresident / concurrent;
+    if (waves > 1 && (cap < 1 || P.N / (cap < 1 ? 1 : cap) < 4096)) cap = ctx->refine_coresident / (jobs_hint > 0 ? jobs_hint : 1);
     if (cap < 1) cap = 1;
     if (g > cap) g = cap;
     return g;
@@ -372,9 +381,10 @@ int run_refine(esacb200_ctx* ctx, const Plan& pl, const Pose* in, Pose* out, con
     if (n_groups < 1) n_groups = 1;
     CK(ctx->masks.ensure((size_t)max_jobs * 2 * words * 4));
     CK(ctx->rounds.ensure((size_t)max_jobs * 2 * 4));
-    CK(ctx->scratch.ensure((size_t)n_groups * group * 2 * 32 * 8));
-    CK(ctx->barrier.ensure((size_t)n_groups * 4));
-    CK(cudaMemsetAsync(ctx->barrier.p, 0, (size_t)n_groups * 4, ctx->stream));
+    CK(ctx->scratch.ensure(refine_scratch_doubles(n_groups, group) * 8));
+    const size_t n_flags = refine_flag_words(n_groups, group);
+    CK(ctx->barrier.ensure((n_flags + 4) * 4));
+    CK(cudaMemsetAsync(ctx->barrier.p, 0, (n_flags + 4) * 4, ctx->stream));
     RefineArgs a;
     a.coords = pl.d_coords;
     a.centres = ctx->centres.as<float>();
@@ -389,7 +399,15 @@ int run_refine(esacb200_ctx* ctx, const Plan& pl, const Pose* in, Pose* out, con
     a.rounds = ctx->rounds.as<int>();
     a.scratch = ctx->scratch.as<double>();
     a.barrier = ctx->barrier.as<unsigned int>();
+    a.job_counter = (int*)(ctx->barrier.as<unsigned int>() + n_flags);
     a.group = group;
+    a.cache = ((words + group - 1) / group) <= refine_cache_words() ? 1 : 0;
+    a.prof = nullptr;
+    if (ctx->refine_profile) {
+        CK(ctx->prof.ensure(16 * 8));
+        CK(cudaMemsetAsync(ctx->prof.p, 0, 16 * 8, ctx->stream));
+        a.prof = ctx->prof.as<long long>();
+    }
     a.P = P;
     a.max_ref_steps = ctx->max_ref_steps;
     launch_refine(a, n_groups, ctx->stream);
@@ -510,7 +528,7 @@ void esacb200_destroy(esacb200_ctx* ctx) {
                       &ctx->slot_of, &ctx->chunks, &ctx->scalars, &ctx->centres, &ctx->poses, &ctx->poses_ref, &ctx->cells,
                       &ctx->tries, &ctx->posepk, &ctx->part, &ctx->scores, &ctx->probs, &ctx->stats, &ctx->contrib,
                       &ctx->masks, &ctx->rounds, &ctx->scratch, &ctx->barrier, &ctx->out17, &ctx->inject, &ctx->losses,
-                      &ctx->red, &ctx->hypgrad, &ctx->job_of, &ctx->gt, &ctx->smp_int, &ctx->smp_surv, &ctx->coords4, &ctx->coords_alt, &ctx->assign64_alt, &ctx->out_batch};
+                      &ctx->red, &ctx->hypgrad, &ctx->job_of, &ctx->gt, &ctx->smp_int, &ctx->smp_surv, &ctx->coords4, &ctx->coords_alt, &ctx->assign64_alt, &ctx->out_batch, &ctx->prof};
     for (DevBuf* b : bufs) b->release();
     for (int i = 0; i < EV_COUNT; ++i)
         if (ctx->ev[i]) cudaEventDestroy(ctx->ev[i]);
@@ -549,6 +567,8 @@ int esacb200_set_option(esacb200_ctx* ctx, const char* key, double v) {
     else if (!strcmp(key, "max_ref_steps")) ctx->max_ref_steps = v < 0 ? 0 : (int)v;
     else if (!strcmp(key, "fixed_seed")) ctx->fixed_seed = v != 0;
     else if (!strcmp(key, "refine_group")) ctx->refine_group_opt = (int)v;
+    else if (!strcmp(key, "refine_profile")) ctx->refine_profile = v != 0;
+    else if (!strcmp(key, "refine_jobs_per_group")) ctx->refine_jobs_per_group = v < 1 ? 1 : (int)v;
     else if (!strcmp(key, "sample_prefilter")) ctx->sample_prefilter = v != 0;
     else if (!strcmp(key, "upload_split")) ctx->upload_split = v != 0;  // host maps in two halves, sampling under the second copy
     else if (!strcmp(key, "sample_groups")) ctx->sample_groups = v >= 2 ? 2 : 1;  // 2: two interleaved lanes on two streams
@@ -993,6 +1013,7 @@ int esacb200_backward_batch(esacb200_ctx* ctx, int B, const float* coords, float
         w->max_tries = ctx->max_tries;
         w->max_ref_steps = ctx->max_ref_steps;
         w->refine_group_opt = ctx->refine_group_opt;
+        w->refine_jobs_per_group = ctx->refine_jobs_per_group;
         w->sample_prefilter = ctx->sample_prefilter;
         w->hyp_offset = ctx->hyp_offset;
         w->score_ppt_opt = ctx->score_ppt_opt;
@@ -1153,6 +1174,14 @@ int esacb200_copy_last_scores(esacb200_ctx* ctx, double* dst, int M) try {
     if (M != ctx->last_M) return fail(ctx, ESACB200_ERR_ARG, "last call had M=%d, asked for %d", ctx->last_M, M);
     CK(cudaMemcpyAsync(dst, ctx->scores.p, (size_t)M * 8, cudaMemcpyDefault, ctx->stream));
     if (!is_device_ptr(dst)) CK(cudaStreamSynchronize(ctx->stream));
+    return ESACB200_OK;
+} ESAC_ABI_CATCH(ctx)
+
+int esacb200_get_refine_profile(esacb200_ctx* ctx, long long* out16) try {
+    if (!ctx || !out16) return ESACB200_ERR_ARG;
+    DeviceGuard device_guard(ctx->device);
+    if (!ctx->prof.p) return fail(ctx, ESACB200_ERR_ARG, "no refinement ran with option refine_profile = 1");
+    CK(cudaMemcpy(out16, ctx->prof.p, 16 * 8, cudaMemcpyDeviceToHost));
     return ESACB200_OK;
 } ESAC_ABI_CATCH(ctx)
 

@@ -130,13 +130,19 @@ struct RefineArgs {
     int mask_words;          // words per job
     int* rounds;
     double* scratch;         // cross-CTA reduction slots
-    unsigned int* barrier;   // cross-CTA barrier counters, zeroed before launch
+    unsigned int* barrier;   // per group: one epoch flag per block + the root's command flag, zeroed before launch
+    int* job_counter;        // next job to hand out (dynamic scheduling), zeroed before launch
     int group;               // CTAs cooperating on one job
+    int cache;               // 1: every CTA's share of the map fits the shared-memory cell cache
+    long long* prof;         // diagnostics: 16 cycle counters of block 0 (null = off)
     Problem P;
     int max_ref_steps;
 };
 void launch_refine(const RefineArgs& a, int n_groups, cudaStream_t st);
 int refine_max_coresident_blocks(int sm_count);
+int refine_cache_words();
+size_t refine_scratch_doubles(int n_groups, int group);
+size_t refine_flag_words(int n_groups, int group);
 // camera->world 4x4 float of poses[*winner] packed for one D2H copy: out[0..15], out[16] = expert id,
 // out[17] = bad-assignment flag, out[18] = winning hypothesis
 void launch_finish_forward(const Pose* poses, const int* winner, const int* assign32, const int* flags, float* out20,

@@ -48,7 +48,8 @@ int esacb200_set_stream(esacb200_ctx* ctx, void* cuda_stream);
 int esacb200_set_seed(esacb200_ctx* ctx, uint64_t seed);
 /* Options: "max_tries" (esac.cpp:44 MAX_SAMPLING_TRIES, default 1000000), "max_ref_steps"
  * (esac.cpp:45 MAX_REF_STEPS, default 100), "fixed_seed" (1: do not advance the call counter),
- * "refine_group" (CTAs per refinement job, 0 = automatic), "sample_prefilter" (default 1; 0 sends every sampling
+ * "refine_group" (CTAs per refinement job, 0 = automatic), "refine_jobs_per_group" (jobs a group
+ * works through when many hypotheses are refined), "refine_profile", "sample_prefilter" (default 1; 0 sends every sampling
  * try through the exact fp64 path -- the results must not change, only the time), "hyp_offset" (global index of
  * local hypothesis 0 for the minimal-set stream; sharded runs), "score_ppt" / "score_hc" (scoring launch shape). */
 int esacb200_set_option(esacb200_ctx* ctx, const char* key, double value);
@@ -172,6 +173,13 @@ typedef struct {
     int score_ppt, score_grid, refine_group;
 } esacb200_stats;
 int esacb200_get_stats(esacb200_ctx* ctx, esacb200_stats* out);
+
+/* Diagnostics: with option "refine_profile" = 1 block 0 of the refinement kernel accumulates clock64() cycles per phase of
+ * an LM evaluation of the root block: [0] produce + receive the command (Rodrigues of the new parameters), [1] pass over
+ * the cells, [2] block reduction + slot write + change of variables, [3] wait for the group's epoch flags, [4] slot
+ * summation, [5] map the sums to (rvec, tvec), [6] accept / reject + LM step; [8] = number of evaluations.
+ * out16: host long long [16]. */
+int esacb200_get_refine_profile(esacb200_ctx* ctx, long long* out16);
 
 /* Read back intermediates of the last forward/backward call (any pointer may be NULL):
  * poses6 double [M][6] initial hypotheses, cells int32 [M][4][2], tries int32 [M], scores / probs double [M],
