@@ -62,8 +62,18 @@ def load_library() -> C.CDLL:
     lib.esacb200_backward.argtypes = [vp, vp, vp, i32, i32, i32, vp, i64, i32, vp, f32, f32, f32] + cam + [C.POINTER(f64)]
     lib.esacb200_forward_batch.argtypes = [vp, i32, vp, i32, i32, i32, vp, i64, i32, vp] + cam + [vp]
     lib.esacb200_forward_batch.restype = i32
-    lib.esacb200_forward_pack.argtypes = [vp, vp, i32, i32, i32, vp, i64, i32] + cam + [i32, vp]
+    lib.esacb200_forward_pack.argtypes = [vp, vp, i32, i32, i32, vp, i64, i32, i32] + cam + [i32, vp]
     lib.esacb200_forward_pack.restype = i32
+    lib.esacb200_nccl_unique_id.argtypes = [vp]
+    lib.esacb200_nccl_unique_id.restype = i32
+    lib.esacb200_comm_init.argtypes = [vp, i32, i32, vp]
+    lib.esacb200_comm_init.restype = i32
+    lib.esacb200_comm_destroy.argtypes = [vp]
+    lib.esacb200_comm_destroy.restype = i32
+    lib.esacb200_forward_sharded.argtypes = [vp, vp, i32, i32, i32, vp, i64, i32, i32, vp] + cam + [i32, C.POINTER(i32)]
+    lib.esacb200_forward_sharded.restype = i32
+    lib.esacb200_backward_sharded_nccl.argtypes = [vp, vp, vp, i32, i32, i32, vp, i64, i32, vp, f32, f32, f32] + cam + [C.POINTER(f64)]
+    lib.esacb200_backward_sharded_nccl.restype = i32
     lib.esacb200_backward_batch.argtypes = ([vp, i32, vp, vp, i32, i32, i32, vp, i64, i32, vp, f32, f32, f32, vp, vp] + cam[2:] +
                                              [vp])
     lib.esacb200_backward_batch.restype = i32
@@ -130,6 +140,7 @@ class Context:
                                "this implementation has no CPU path")
         self.handle = h
         self.device = int(device)
+        self.comm_world, self.comm_rank = 1, 0
 
     def close(self):
         if getattr(self, "handle", None):
@@ -169,6 +180,16 @@ class Context:
         s = Stats()
         self.check(self.lib.esacb200_get_stats(self.handle, C.byref(s)))
         return s.as_dict()
+
+    def comm_init(self, world: int, rank: int, unique_id: bytes):
+        """ncclCommInitRank inside the library (collective over all ranks); unique_id from nccl_unique_id() of rank 0."""
+        buf = C.create_string_buffer(bytes(unique_id), 128)
+        self.check(self.lib.esacb200_comm_init(self.handle, int(world), int(rank), buf))
+        self.comm_world, self.comm_rank = int(world), int(rank)
+
+    def comm_destroy(self):
+        self.check(self.lib.esacb200_comm_destroy(self.handle))
+        self.comm_world, self.comm_rank = 1, 0
 
     def refine_profile(self) -> np.ndarray:
         """Phase cycle counters of the last refinement (option "refine_profile" = 1), see include/esac_b200.h."""
@@ -311,6 +332,13 @@ def _pick_ctx(*devices) -> Context:
         import torch
         stream = torch.cuda.current_stream(ctx.device).cuda_stream or _CUDA_STREAM_LEGACY
     ctx.set_stream(stream)
+    return ctx
+
+
+def _pick_ctx_host(device: int | None) -> Context:
+    """Context for host-only arguments on an explicit device (sharded entry points: one process per GPU)."""
+    ctx = context(device)
+    ctx.set_stream(0)
     return ctx
 
 
@@ -547,24 +575,95 @@ def reproj_loss(prediction, gtPoses, focalLength, padX, padY, cutLoss, subSampli
     return [float(v) for v in losses]
 
 
-def forward_pack(sceneCoordinates, hypAssignment, params, expert_offset: int, pack_out):
+def nccl_unique_id() -> bytes:
+    """128-byte ncclUniqueId (call on one rank, distribute to the others, then Context.comm_init on every rank)."""
+    buf = C.create_string_buffer(128)
+    rc = load_library().esacb200_nccl_unique_id(buf)
+    if rc != 0:
+        raise RuntimeError(f"esac_b200: ncclGetUniqueId failed (status {rc}); is libnccl.so.2 loadable?")
+    return buf.raw
+
+
+def forward_pack(sceneCoordinates, hypAssignment, params, expert_offset: int, pack_out, M_pad: int | None = None):
     """The local half of a sharded forward, enqueued on the current CUDA stream without a host synchronisation
     (esacb200_forward_pack).  sceneCoordinates [E,3,H,W] / hypAssignment [M] are CUDA tensors, params the positional tail of
-    esac.forward (shiftX .. subSampling), pack_out a CUDA float64 tensor of M + 18 elements (see include/esac_b200.h)."""
+    esac.forward (shiftX .. subSampling), pack_out a CUDA float64 tensor of M_pad + 19 elements (see include/esac_b200.h);
+    M_pad (default M) = the largest M of any shard."""
     _check(sceneCoordinates, "Float", 4, "sceneCoordinates")
     _check(hypAssignment, "Long", 1, "hypAssignment")
     if not (_is_torch(sceneCoordinates) and sceneCoordinates.is_cuda and hypAssignment.is_cuda and pack_out.is_cuda):
         raise RuntimeError("forward_pack takes CUDA tensors")
     co = _Arg(sceneCoordinates)
     aptr, astride, M, adev, _keep = _assign_arg(hypAssignment)
-    if pack_out.dtype != __import__("torch").float64 or pack_out.numel() != M + 18 or not pack_out.is_contiguous():
-        raise RuntimeError("pack_out must be a contiguous float64 tensor of M + 18 elements")
+    M_pad = M if M_pad is None else int(M_pad)
+    if pack_out.dtype != __import__("torch").float64 or pack_out.numel() != M_pad + 19 or not pack_out.is_contiguous():
+        raise RuntimeError("pack_out must be a contiguous float64 tensor of M_pad + 19 elements")
     ctx = _pick_ctx(co.device, adev, pack_out.device.index)
     E, _, H, W = (int(v) for v in sceneCoordinates.shape)
     shiftX, shiftY, f, ppx, ppy, tau, alpha, beta, maxReproj, sub = params
-    ctx.check(ctx.lib.esacb200_forward_pack(ctx.handle, co.ptr, E, H, W, aptr, astride, M, int(shiftX), int(shiftY), float(f),
+    ctx.check(ctx.lib.esacb200_forward_pack(ctx.handle, co.ptr, E, H, W, aptr, astride, M, M_pad, int(shiftX), int(shiftY), float(f),
                                             float(ppx), float(ppy), float(tau), float(alpha), float(beta), float(maxReproj),
                                             int(sub), int(expert_offset), pack_out.data_ptr()))
+
+
+def forward_sharded(sceneCoordinates, hypAssignment, outPose, shiftX, shiftY, focalLength, ppointX, ppointY, inlierThreshold,
+                    inlierAlpha, inlierBeta, maxReproj, subSampling, expert_offset: int = 0, M_pad: int | None = None,
+                    hyp_offset: int = 0, device: int | None = None) -> int:
+    """esac.forward over experts / hypotheses sharded across the ranks of the library's communicator (Context.comm_init):
+    this rank's shard in, the GLOBAL winner's pose (outPose, in place) and expert index out, on every rank.  One
+    ncclAllGather on the library's stream, no torch collective.  hypAssignment may be empty (M = 0)."""
+    _check(sceneCoordinates, "Float", 4, "sceneCoordinates")
+    _check(hypAssignment, "Long", 1, "hypAssignment")
+    _check(outPose, "Float", 2, "outPose")
+    co = _Arg(sceneCoordinates)
+    op = _Arg(outPose, writable=True)
+    aptr, astride, M, adev, _keep = _assign_arg(hypAssignment)
+    M_pad = max(M, 1) if M_pad is None else int(M_pad)
+    devs = [d for d in (co.device, op.device, adev) if d is not None]
+    ctx = _pick_ctx(*devs) if devs else _pick_ctx_host(device)
+    E, _, H, W = (int(s) for s in sceneCoordinates.shape)
+    expert = C.c_int(-1)
+    ctx.set_option("hyp_offset", hyp_offset)
+    try:
+        rc = ctx.lib.esacb200_forward_sharded(ctx.handle, co.ptr, E, H, W, aptr, astride, M, M_pad, op.ptr, int(shiftX), int(shiftY),
+                                              float(focalLength), float(ppointX), float(ppointY), float(inlierThreshold),
+                                              float(inlierAlpha), float(inlierBeta), float(maxReproj), int(subSampling),
+                                              int(expert_offset), C.byref(expert))
+    finally:
+        ctx.set_option("hyp_offset", 0)
+    ctx.check(rc)
+    op.finish()
+    return int(expert.value)
+
+
+def backward_sharded_nccl(sceneCoordinates, outGradients, hypAssignment, gtPose, wLossRot, wLossTrans, lossCut, shiftX, shiftY,
+                          focalLength, ppointX, ppointY, inlierThreshold, inlierAlpha, inlierBeta, maxReproj, subSampling,
+                          hyp_offset: int = 0, device: int | None = None) -> float:
+    """esac.backward on this rank's shard; the two exchanges run as NCCL collectives inside the library.  Returns the GLOBAL
+    expected loss; outGradients receives this shard's gradient slices.  hypAssignment may be empty."""
+    _check(sceneCoordinates, "Float", 4, "sceneCoordinates")
+    _check(outGradients, "Float", 4, "outGradients")
+    _check(hypAssignment, "Long", 1, "hypAssignment")
+    _check(gtPose, "Float", 2, "gtPose")
+    co = _Arg(sceneCoordinates)
+    gr = _Arg(outGradients, writable=True)
+    gt = _Arg(gtPose)
+    aptr, astride, M, adev, _keep = _assign_arg(hypAssignment)
+    devs = [d for d in (co.device, gr.device, gt.device, adev) if d is not None]
+    ctx = _pick_ctx(*devs) if devs else _pick_ctx_host(device)
+    E, _, H, W = (int(s) for s in sceneCoordinates.shape)
+    loss = C.c_double(0.0)
+    ctx.set_option("hyp_offset", hyp_offset)
+    try:
+        rc = ctx.lib.esacb200_backward_sharded_nccl(ctx.handle, co.ptr, gr.ptr, E, H, W, aptr, astride, M, gt.ptr, float(wLossRot),
+                                                    float(wLossTrans), float(lossCut), int(shiftX), int(shiftY), float(focalLength),
+                                                    float(ppointX), float(ppointY), float(inlierThreshold), float(inlierAlpha),
+                                                    float(inlierBeta), float(maxReproj), int(subSampling), C.byref(loss))
+    finally:
+        ctx.set_option("hyp_offset", 0)
+    ctx.check(rc)
+    gr.finish()
+    return float(loss.value)
 
 
 

@@ -4,6 +4,7 @@
 // stage; every stage is a CUDA kernel launched on one stream with no host round trip until the final
 // 68-byte (forward) / 8-byte (backward) result copy.
 #include <cuda_runtime.h>
+#include <dlfcn.h>
 #include <stdarg.h>
 #include <stdio.h>
 #include <stdlib.h>
@@ -89,6 +90,10 @@ struct esacb200_ctx {
     int last_M = 0;
     bool last_backward = false;
     int batch_workers = 8;
+    // NCCL communicator of the sharded entry points (esacb200_comm_init); the library is resolved at run time with dlopen
+    void* nccl_comm = nullptr;
+    int comm_world = 1, comm_rank = 0;
+    DevBuf gathered;
     std::vector<esacb200_ctx*> workers;  // lazily created contexts of esacb200_backward_batch (own stream + workspace each)
 };
 
@@ -108,6 +113,51 @@ struct DeviceGuard {
     DeviceGuard(const DeviceGuard&) = delete;
     DeviceGuard& operator=(const DeviceGuard&) = delete;
 };
+
+// ---- NCCL, resolved at run time ---------------------------------------------------------------------------------
+// The library must load on machines without NCCL (the CPU test box) and must share the NCCL instance the host process already
+// holds (torch bundles its own libnccl.so.2): no link-time dependency, dlopen of the soname instead -- RTLD_NOLOAD first, so an
+// already loaded copy is reused.  Only the five entry points below are needed; their prototypes are NCCL's public ABI.
+struct NcclApi {
+    typedef struct { char internal[128]; } UniqueId;
+    int (*GetUniqueId)(UniqueId*) = nullptr;
+    int (*CommInitRank)(void**, int, UniqueId, int) = nullptr;
+    int (*CommDestroy)(void*) = nullptr;
+    int (*AllGather)(const void*, void*, size_t, int, void*, cudaStream_t) = nullptr;
+    int (*AllReduce)(const void*, void*, size_t, int, int, void*, cudaStream_t) = nullptr;
+    const char* (*GetErrorString)(int) = nullptr;
+    bool ok = false;
+};
+constexpr int kNcclFloat64 = 8;  // ncclDouble
+constexpr int kNcclSum = 0;      // ncclSum
+
+NcclApi& nccl_api() {
+    static NcclApi api;
+    static bool tried = false;
+    if (tried) return api;
+    tried = true;
+    void* h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_NOLOAD | RTLD_GLOBAL);
+    if (!h) h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+    if (!h) h = dlopen("libnccl.so", RTLD_NOW | RTLD_GLOBAL);
+    if (!h) return api;
+    api.GetUniqueId = (int (*)(NcclApi::UniqueId*))dlsym(h, "ncclGetUniqueId");
+    api.CommInitRank = (int (*)(void**, int, NcclApi::UniqueId, int))dlsym(h, "ncclCommInitRank");
+    api.CommDestroy = (int (*)(void*))dlsym(h, "ncclCommDestroy");
+    api.AllGather = (int (*)(const void*, void*, size_t, int, void*, cudaStream_t))dlsym(h, "ncclAllGather");
+    api.AllReduce = (int (*)(const void*, void*, size_t, int, int, void*, cudaStream_t))dlsym(h, "ncclAllReduce");
+    api.GetErrorString = (const char* (*)(int))dlsym(h, "ncclGetErrorString");
+    api.ok = api.GetUniqueId && api.CommInitRank && api.CommDestroy && api.AllGather && api.AllReduce;
+    return api;
+}
+
+int fail(esacb200_ctx* c, int code, const char* fmt, ...);
+#define CKN(call)                                                                                              \
+    do {                                                                                                       \
+        int r__ = (call);                                                                                      \
+        if (r__ != 0)                                                                                          \
+            return fail(ctx, ESACB200_ERR_CUDA, "%s failed: %s (%s:%d)", #call,                                \
+                        nccl_api().GetErrorString ? nccl_api().GetErrorString(r__) : "NCCL error", __FILE__, __LINE__); \
+    } while (0)
 
 int fail(esacb200_ctx* c, int code, const char* fmt, ...) {
     va_list ap;
@@ -523,12 +573,13 @@ void esacb200_destroy(esacb200_ctx* ctx) {
     for (esacb200_ctx* w : ctx->workers) esacb200_destroy(w);
     ctx->workers.clear();
     DeviceGuard device_guard(ctx->device);
+    if (ctx->nccl_comm) { cudaStreamSynchronize(ctx->stream); nccl_api().CommDestroy(ctx->nccl_comm); ctx->nccl_comm = nullptr; }
     cudaStreamSynchronize(ctx->stream);
     DevBuf* bufs[] = {&ctx->coords, &ctx->grads, &ctx->assign64, &ctx->assign32, &ctx->counts, &ctx->offsets, &ctx->perm,
                       &ctx->slot_of, &ctx->chunks, &ctx->scalars, &ctx->centres, &ctx->poses, &ctx->poses_ref, &ctx->cells,
                       &ctx->tries, &ctx->posepk, &ctx->part, &ctx->scores, &ctx->probs, &ctx->stats, &ctx->contrib,
                       &ctx->masks, &ctx->rounds, &ctx->scratch, &ctx->barrier, &ctx->out17, &ctx->inject, &ctx->losses,
-                      &ctx->red, &ctx->hypgrad, &ctx->job_of, &ctx->gt, &ctx->smp_int, &ctx->smp_surv, &ctx->coords4, &ctx->coords_alt, &ctx->assign64_alt, &ctx->out_batch, &ctx->prof};
+                      &ctx->red, &ctx->hypgrad, &ctx->job_of, &ctx->gt, &ctx->smp_int, &ctx->smp_surv, &ctx->coords4, &ctx->coords_alt, &ctx->assign64_alt, &ctx->out_batch, &ctx->prof, &ctx->gathered};
     for (DevBuf* b : bufs) b->release();
     for (int i = 0; i < EV_COUNT; ++i)
         if (ctx->ev[i]) cudaEventDestroy(ctx->ev[i]);
@@ -644,32 +695,123 @@ int esacb200_forward(esacb200_ctx* ctx, const float* coords, int E, int H, int W
 } ESAC_ABI_CATCH(ctx)
 
 // -------------------------------------------------------------------------------------------------
-int esacb200_forward_pack(esacb200_ctx* ctx, const float* coords, int E, int H, int W, const int64_t* assign,
-                          int64_t assign_stride, int M, int shiftX, int shiftY, float f, float ppx, float ppy, float tau,
-                          float alpha, float beta, float maxReproj, int sub, int expert_offset, double* pack_out) try {
-    if (!ctx) return ESACB200_ERR_ARG;
-    DeviceGuard device_guard(ctx->device);
-    if (!coords || !assign || !pack_out) return fail(ctx, ESACB200_ERR_ARG, "null pointer argument");
-    if (!is_device_ptr(coords) || !is_device_ptr(assign) || !is_device_ptr(pack_out))
-        return fail(ctx, ESACB200_ERR_ARG, "forward_pack takes device pointers only");
-    Plan pl;
-    int rc = fill_problem(ctx, pl.P, E, H, W, M, shiftX, shiftY, f, ppx, ppy, tau, alpha, beta, maxReproj, sub);
-    if (rc) return rc;
-    if ((long long)(W - 1) * (H - 1) < 4) return fail(ctx, ESACB200_ERR_ARG, "map %dx%d too small", W, H);
+// local half of a sharded forward: pipeline + record, no synchronisation (shared by forward_pack and forward_sharded)
+static int enqueue_forward_record(esacb200_ctx* ctx, const float* coords, int E, int H, int W, const int64_t* assign,
+                                  int64_t assign_stride, int M, int M_pad, int shiftX, int shiftY, float f, float ppx, float ppy,
+                                  float tau, float alpha, float beta, float maxReproj, int sub, int expert_offset, double* pack_out) {
+    if (M_pad < M || M_pad < 1) return fail(ctx, ESACB200_ERR_ARG, "M_pad (%d) must be >= M (%d) and >= 1", M_pad, M);
     begin_call(ctx);
     ctx->inj_M = ctx->inj_T = 0;
-    rc = stage_inputs(ctx, pl, coords, assign, assign_stride);
-    if (rc) return rc;
-    rc = enqueue_forward_core(ctx, pl, ctx->out17.as<float>());
-    if (rc) return rc;
-    launch_pack_forward(ctx->scores.as<double>(), ctx->out17.as<float>(), M, expert_offset, pack_out, ctx->stream);
+    if (M > 0) {
+        Plan pl;
+        int rc = fill_problem(ctx, pl.P, E, H, W, M, shiftX, shiftY, f, ppx, ppy, tau, alpha, beta, maxReproj, sub);
+        if (rc) return rc;
+        if ((long long)(W - 1) * (H - 1) < 4) return fail(ctx, ESACB200_ERR_ARG, "map %dx%d too small", W, H);
+        rc = stage_inputs(ctx, pl, coords, assign, assign_stride);
+        if (rc) return rc;
+        rc = enqueue_forward_core(ctx, pl, ctx->out17.as<float>());
+        if (rc) return rc;
+    } else {
+        CK(ctx->scores.ensure(8));
+        CK(ctx->out17.ensure(32 * 4));
+    }
+    launch_pack_forward(ctx->scores.as<double>(), ctx->out17.as<float>(), M, M_pad, expert_offset, pack_out, ctx->stream);
     CK(cudaGetLastError());
     ctx->st.kernel_launches += 1;
-    mark(ctx, EV_END);
     ctx->st.M = M;
     ctx->last_M = M;
     ctx->last_backward = false;
+    return ESACB200_OK;
+}
+
+int esacb200_forward_pack(esacb200_ctx* ctx, const float* coords, int E, int H, int W, const int64_t* assign,
+                          int64_t assign_stride, int M, int M_pad, int shiftX, int shiftY, float f, float ppx, float ppy, float tau,
+                          float alpha, float beta, float maxReproj, int sub, int expert_offset, double* pack_out) try {
+    if (!ctx) return ESACB200_ERR_ARG;
+    DeviceGuard device_guard(ctx->device);
+    if (!pack_out || (M > 0 && (!coords || !assign))) return fail(ctx, ESACB200_ERR_ARG, "null pointer argument");
+    if ((M > 0 && (!is_device_ptr(coords) || !is_device_ptr(assign))) || !is_device_ptr(pack_out))
+        return fail(ctx, ESACB200_ERR_ARG, "forward_pack takes device pointers only");
+    int rc = enqueue_forward_record(ctx, coords, E, H, W, assign, assign_stride, M, M_pad, shiftX, shiftY, f, ppx, ppy, tau, alpha,
+                                    beta, maxReproj, sub, expert_offset, pack_out);
+    if (rc) return rc;
+    mark(ctx, EV_END);
     return ESACB200_OK;   // stage timers of this call are not collected: that would need the synchronisation
+} ESAC_ABI_CATCH(ctx)
+
+// ---- communicator -----------------------------------------------------------------------------------
+int esacb200_nccl_unique_id(void* out128) {
+    if (!out128) return ESACB200_ERR_ARG;
+    NcclApi& n = nccl_api();
+    if (!n.ok) return ESACB200_ERR_NO_DEVICE;
+    NcclApi::UniqueId id;
+    if (n.GetUniqueId(&id) != 0) return ESACB200_ERR_CUDA;
+    memcpy(out128, id.internal, 128);
+    return ESACB200_OK;
+}
+
+int esacb200_comm_init(esacb200_ctx* ctx, int world, int rank, const void* id128) try {
+    if (!ctx) return ESACB200_ERR_ARG;
+    DeviceGuard device_guard(ctx->device);
+    if (!id128 || world < 1 || rank < 0 || rank >= world) return fail(ctx, ESACB200_ERR_ARG, "bad communicator arguments");
+    NcclApi& n = nccl_api();
+    if (!n.ok) return fail(ctx, ESACB200_ERR_NO_DEVICE, "libnccl.so.2 cannot be loaded");
+    if (ctx->nccl_comm) { n.CommDestroy(ctx->nccl_comm); ctx->nccl_comm = nullptr; }
+    NcclApi::UniqueId id;
+    memcpy(id.internal, id128, 128);
+    CKN(n.CommInitRank(&ctx->nccl_comm, world, id, rank));
+    ctx->comm_world = world;
+    ctx->comm_rank = rank;
+    return ESACB200_OK;
+} ESAC_ABI_CATCH(ctx)
+
+int esacb200_comm_destroy(esacb200_ctx* ctx) {
+    if (!ctx) return ESACB200_ERR_ARG;
+    DeviceGuard device_guard(ctx->device);
+    if (ctx->nccl_comm) {
+        cudaStreamSynchronize(ctx->stream);
+        nccl_api().CommDestroy(ctx->nccl_comm);
+        ctx->nccl_comm = nullptr;
+    }
+    ctx->comm_world = 1;
+    ctx->comm_rank = 0;
+    return ESACB200_OK;
+}
+
+// esac_forward with the experts / hypotheses sharded over the ranks of the communicator: local pipeline ->
+// record -> ONE ncclAllGather on the context's stream -> softMax / draw over all records on the device -> one 80-byte
+// read-back.  Every rank returns the global winner's pose and expert.  M may be 0 (a shard without hypotheses); M_pad is
+// the largest M of any rank (records must have one size).
+int esacb200_forward_sharded(esacb200_ctx* ctx, const float* coords, int E, int H, int W, const int64_t* assign,
+                             int64_t assign_stride, int M, int M_pad, float* out_pose, int shiftX, int shiftY, float f, float ppx,
+                             float ppy, float tau, float alpha, float beta, float maxReproj, int sub, int expert_offset,
+                             int* out_expert) try {
+    if (!ctx) return ESACB200_ERR_ARG;
+    DeviceGuard device_guard(ctx->device);
+    if (!ctx->nccl_comm) return fail(ctx, ESACB200_ERR_ARG, "no communicator: call esacb200_comm_init first");
+    if (!out_pose || (M > 0 && (!coords || !assign))) return fail(ctx, ESACB200_ERR_ARG, "null pointer argument");
+    const int world = ctx->comm_world;
+    const size_t rec = (size_t)M_pad + 19;
+    CK(ctx->gathered.ensure((world + 1) * rec * 8));
+    double* mine = ctx->gathered.as<double>() + (size_t)world * rec;
+    int rc = enqueue_forward_record(ctx, coords, E, H, W, assign, assign_stride, M, M_pad, shiftX, shiftY, f, ppx, ppy, tau, alpha,
+                                    beta, maxReproj, sub, expert_offset, mine);
+    if (rc) return rc;
+    CKN(nccl_api().AllGather(mine, ctx->gathered.p, rec, kNcclFloat64, ctx->nccl_comm, ctx->stream));
+    launch_select_gathered(ctx->gathered.as<double>(), world, M_pad, ctx->out17.as<float>(), ctx->stream);
+    CK(cudaGetLastError());
+    ctx->st.kernel_launches += 2;
+    CK(cudaMemcpyAsync(ctx->h_out, ctx->out17.p, 20 * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
+    if (is_device_ptr(out_pose)) CK(cudaMemcpyAsync(out_pose, ctx->out17.p, 16 * sizeof(float), cudaMemcpyDeviceToDevice, ctx->stream));
+    mark(ctx, EV_END);
+    CK(cudaStreamSynchronize(ctx->stream));
+    CK(cudaGetLastError());
+    if (ctx->h_out[17] != 0.f) return fail(ctx, ESACB200_ERR_ARG, "a shard's hypAssignment holds an expert index outside its experts");
+    if (!is_device_ptr(out_pose)) memcpy(out_pose, ctx->h_out, 16 * sizeof(float));
+    if (out_expert) *out_expert = (int)ctx->h_out[16];
+    ctx->st.winner = (int)ctx->h_out[18];
+    finish_stats(ctx);
+    return ESACB200_OK;
 } ESAC_ABI_CATCH(ctx)
 
 // -------------------------------------------------------------------------------------------------
@@ -828,7 +970,7 @@ int esacb200_refine_poses(esacb200_ctx* ctx, const float* coords, int E, int H, 
 static int backward_impl(esacb200_ctx* ctx, const float* coords, float* grads, int E, int H, int W, const int64_t* assign,
                          int64_t assign_stride, int M, const float* gt_pose, float wRot, float wTrans, float cut, int shiftX,
                          int shiftY, float f, float ppx, float ppy, float tau, float alpha, float beta, float maxReproj, int sub,
-                         esacb200_exchange_fn exchange, void* user, double* out_loss) {
+                         esacb200_exchange_fn exchange, void* user, double* out_loss, bool use_nccl = false) {
     if (!ctx) return ESACB200_ERR_ARG;
     DeviceGuard device_guard(ctx->device);
     if (!coords || !assign || !grads || !gt_pose) return fail(ctx, ESACB200_ERR_ARG, "null pointer argument");
@@ -864,6 +1006,13 @@ static int backward_impl(esacb200_ctx* ctx, const float* coords, float* grads, i
         launch_rescale_probs(ctx->scores.as<double>(), P, v[0], v[1], ctx->probs.as<double>(), ctx->contrib.as<int>(),
                              sc + S_NCONTRIB, ctx->stream);
         ctx->st.kernel_launches += 1;
+    } else if (use_nccl) {
+        // exchange 1 on the device: all-gather of the (max, sum exp) pairs, merged by the kernel that rebuilds the probabilities
+        CK(ctx->gathered.ensure((size_t)ctx->comm_world * 2 * 8));
+        CKN(nccl_api().AllGather(ctx->stats.as<double>() + 5, ctx->gathered.p, 2, kNcclFloat64, ctx->nccl_comm, ctx->stream));
+        launch_rescale_probs_gathered(ctx->scores.as<double>(), P, ctx->gathered.as<double>(), ctx->comm_world, nullptr,
+                                      ctx->probs.as<double>(), ctx->contrib.as<int>(), sc + S_NCONTRIB, ctx->stream);
+        ctx->st.kernel_launches += 2;
     }
     // refHyps = initHyps for everything below PROB_THRESH (esac.cpp:331-334)
     CK(cudaMemcpyAsync(ctx->poses_ref.p, ctx->poses.p, (size_t)M * sizeof(Pose), cudaMemcpyDeviceToDevice, ctx->stream));
@@ -927,6 +1076,13 @@ static int backward_impl(esacb200_ctx* ctx, const float* coords, float* grads, i
         CK(cudaMemcpyAsync(ctx->stats.as<double>() + 7, ctx->h_dbl + 6, sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
         b.expected_override = ctx->stats.as<double>() + 7;
         ctx->st.kernel_launches += 1;
+    } else if (use_nccl) {
+        // exchange 2 on the device: all-reduce of the partial expectations, no host round trip
+        launch_backward_losses(b, ctx->stream);
+        CKN(nccl_api().AllReduce(ctx->stats.as<double>() + 4, ctx->stats.as<double>() + 7, 1, kNcclFloat64, kNcclSum, ctx->nccl_comm,
+                                 ctx->stream));
+        b.expected_override = ctx->stats.as<double>() + 7;
+        ctx->st.kernel_launches += 2;
     }
     launch_backward(b, M, ctx->stream);
     CK(cudaGetLastError());
@@ -934,18 +1090,19 @@ static int backward_impl(esacb200_ctx* ctx, const float* coords, float* grads, i
     mark(ctx, EV_BWD);
     if (grads_on_host) CK(cudaMemcpyAsync(grads, d_grads, cbytes, cudaMemcpyDeviceToHost, ctx->stream));
     CK(cudaMemcpyAsync(ctx->h_out + 20, sc, 8 * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
-    CK(cudaMemcpyAsync(ctx->h_dbl, ctx->stats.p, 5 * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaMemcpyAsync(ctx->h_dbl, ctx->stats.p, 8 * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
     mark(ctx, EV_END);
     CK(cudaStreamSynchronize(ctx->stream));
     CK(cudaGetLastError());
     const int* hs = (const int*)(ctx->h_out + 20);
     if (hs[S_FLAGS]) return fail(ctx, ESACB200_ERR_ARG, "hypAssignment holds an expert index outside [0, %d)", E);
-    if (out_loss) *out_loss = exchange ? global_loss : ctx->h_dbl[4];
+    if (use_nccl) global_loss = ctx->h_dbl[7];
+    if (out_loss) *out_loss = (exchange || use_nccl) ? global_loss : ctx->h_dbl[4];
     ctx->st.M = M;
     ctx->st.winner = hs[S_WINNER];
     ctx->st.n_contrib = hs[S_NCONTRIB];
     ctx->st.entropy = ctx->h_dbl[0];
-    ctx->st.expected_loss = exchange ? global_loss : ctx->h_dbl[4];
+    ctx->st.expected_loss = (exchange || use_nccl) ? global_loss : ctx->h_dbl[4];
     ctx->last_M = M;
     ctx->last_backward = true;
     finish_stats(ctx);
@@ -968,6 +1125,38 @@ int esacb200_backward_sharded(esacb200_ctx* ctx, const float* coords, float* gra
     if (!exchange) return ctx ? fail(ctx, ESACB200_ERR_ARG, "exchange callback is null") : ESACB200_ERR_ARG;
     return backward_impl(ctx, coords, grads, E, H, W, assign, assign_stride, M, gt_pose, wRot, wTrans, cut, shiftX, shiftY, f, ppx,
                          ppy, tau, alpha, beta, maxReproj, sub, exchange, user, out_loss);
+} ESAC_ABI_CATCH(ctx)
+
+// esac_backward with the experts / hypotheses sharded over the ranks of the communicator: the two exchanges of the path
+//  run as NCCL collectives on the context's stream -- an all-gather of two doubles per rank and an all-reduce of
+// one -- with no host callback.  M may be 0: the rank then only takes part in the collectives.
+int esacb200_backward_sharded_nccl(esacb200_ctx* ctx, const float* coords, float* grads, int E, int H, int W,
+                                   const int64_t* assign, int64_t assign_stride, int M, const float* gt_pose, float wRot,
+                                   float wTrans, float cut, int shiftX, int shiftY, float f, float ppx, float ppy, float tau,
+                                   float alpha, float beta, float maxReproj, int sub, double* out_loss) try {
+    if (!ctx) return ESACB200_ERR_ARG;
+    DeviceGuard device_guard(ctx->device);
+    if (!ctx->nccl_comm) return fail(ctx, ESACB200_ERR_ARG, "no communicator: call esacb200_comm_init first");
+    if (M > 0)
+        return backward_impl(ctx, coords, grads, E, H, W, assign, assign_stride, M, gt_pose, wRot, wTrans, cut, shiftX, shiftY, f, ppx,
+                             ppy, tau, alpha, beta, maxReproj, sub, nullptr, nullptr, out_loss, /*use_nccl=*/true);
+    // no hypotheses here: neutral contributions to both collectives
+    begin_call(ctx);
+    CK(ctx->stats.ensure(8 * 8));
+    CK(ctx->gathered.ensure((size_t)ctx->comm_world * 2 * 8));
+    ctx->h_dbl[0] = 0.; ctx->h_dbl[1] = -1e300; ctx->h_dbl[2] = 0.;  // stats[4] partial expectation, [5] max score, [6] sum exp
+    CK(cudaMemcpyAsync(ctx->stats.as<double>() + 4, ctx->h_dbl, 3 * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+    CKN(nccl_api().AllGather(ctx->stats.as<double>() + 5, ctx->gathered.p, 2, kNcclFloat64, ctx->nccl_comm, ctx->stream));
+    CKN(nccl_api().AllReduce(ctx->stats.as<double>() + 4, ctx->stats.as<double>() + 7, 1, kNcclFloat64, kNcclSum, ctx->nccl_comm,
+                             ctx->stream));
+    CK(cudaMemcpyAsync(ctx->h_dbl + 4, ctx->stats.as<double>() + 7, sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    mark(ctx, EV_END);
+    CK(cudaStreamSynchronize(ctx->stream));
+    if (out_loss) *out_loss = ctx->h_dbl[4];
+    ctx->st.expected_loss = ctx->h_dbl[4];
+    ctx->last_M = 0;
+    finish_stats(ctx);
+    return ESACB200_OK;
 } ESAC_ABI_CATCH(ctx)
 
 // -------------------------------------------------------------------------------------------------

@@ -88,6 +88,8 @@ void launch_select(const float* part, const int* slot_of, const Problem& P, int 
 
 void launch_rescale_probs(const double* scores, const Problem& P, double gmax, double gsum, double* probs, int* contrib,
                           int* n_contrib, cudaStream_t st);
+void launch_rescale_probs_gathered(const double* scores, const Problem& P, const double* pairs, int world, double* norm_out,
+                                   double* probs, int* contrib, int* n_contrib, cudaStream_t st);
 
 // --- hyp.cu -------------------------------------------------------------------------------
 // Work state of the sampling waves (all device memory, M = hypotheses).
@@ -148,7 +150,8 @@ size_t refine_flag_words(int n_groups, int group);
 void launch_finish_forward(const Pose* poses, const int* winner, const int* assign32, const int* flags, float* out20,
                            cudaStream_t st);
 
-void launch_pack_forward(const double* scores, const float* out20, int M, int expert_offset, double* pack, cudaStream_t st);
+void launch_pack_forward(const double* scores, const float* out20, int M, int M_pad, int expert_offset, double* pack, cudaStream_t st);
+void launch_select_gathered(const double* gathered, int world, int M_pad, float* out20, cudaStream_t st);
 
 // --- gating.cu ----------------------------------------------------------------------------
 int assign_max_experts();

@@ -604,4 +604,50 @@ void launch_rescale_probs(const double* scores, const Problem& P, double gmax, d
     rescale_probs_kernel<<<1, 1024, 0, st>>>(scores, P, gmax, gsum, probs, contrib, n_contrib);
 }
 
+// The same with the normalisation merged on the device from the all-gathered (max, sum exp(score - max)) pairs of all ranks
+// (no host round trip): gmax = max_r m_r, gsum = sum_r s_r exp(m_r - gmax), in rank order.  norm_out[0..1] = (gmax, gsum).
+__global__ void __launch_bounds__(1024) rescale_probs_gathered_kernel(const double* __restrict__ scores, Problem P,
+                                                                      const double* __restrict__ pairs, int world, double* norm_out,
+                                                                      double* probs, int* contrib, int* n_contrib) {
+    __shared__ int swc[32];
+    __shared__ int srun;
+    __shared__ double snorm[2];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nw = blockDim.x >> 5;
+    if (tid == 0) {
+        srun = 0;
+        double gmax = -1e300;
+        for (int r = 0; r < world; ++r) gmax = fmax(gmax, pairs[2 * r]);
+        double gsum = 0;
+        for (int r = 0; r < world; ++r) gsum += pairs[2 * r + 1] * exp(pairs[2 * r] - gmax);
+        snorm[0] = gmax; snorm[1] = gsum;
+        if (norm_out) { norm_out[0] = gmax; norm_out[1] = gsum; }
+    }
+    __syncthreads();
+    const double gmax = snorm[0], gsum = snorm[1];
+    for (int b = 0; b < P.M; b += blockDim.x) {
+        const int h = b + tid;
+        bool flag = false;
+        if (h < P.M) {
+            const double p = exp(scores[h] - gmax) / gsum;
+            probs[h] = p;
+            flag = !(p < kProbThresh);
+        }
+        const unsigned m = __ballot_sync(0xffffffffu, flag);
+        if (lane == 0) swc[warp] = __popc(m);
+        __syncthreads();
+        int off = srun;
+        for (int w = 0; w < warp; ++w) off += swc[w];
+        if (flag) contrib[off + __popc(m & ((1u << lane) - 1u))] = h;
+        __syncthreads();
+        if (tid == 0) { int t = 0; for (int w = 0; w < nw; ++w) t += swc[w]; srun += t; }
+        __syncthreads();
+    }
+    if (tid == 0) *n_contrib = srun;
+}
+
+void launch_rescale_probs_gathered(const double* scores, const Problem& P, const double* pairs, int world, double* norm_out,
+                                   double* probs, int* contrib, int* n_contrib, cudaStream_t st) {
+    rescale_probs_gathered_kernel<<<1, 1024, 0, st>>>(scores, P, pairs, world, norm_out, probs, contrib, n_contrib);
+}
+
 }  // namespace esacb200

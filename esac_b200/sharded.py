@@ -1,38 +1,92 @@
-"""Multi-GPU esac.forward: experts sharded expert-major across ranks, ONE all-gather of per-shard scores.
+"""Multi-GPU esac.forward / esac.backward: experts (and with them the hypotheses) sharded across ranks, one process per GPU.
 
-Hypotheses are independent through sampling, P3P, scoring and (per shard) refinement; the only exchange in
-esac_forward is the softmax/argmax over all scores (esac.cpp:153-155).  Every rank therefore runs the complete
-local pipeline on the experts it owns -- including the refinement of its local best hypothesis, which costs no
-extra latency because the ranks run concurrently -- and a single all-gather of
-    [ local scores (M_local) | local refined pose (16) | global expert id | local winner index ]
-lets every rank pick the global winner with the reference's rule (first strict maximum, esac_util.h:519-523).
-Messages are KB-sized: the collective is latency-bound and is issued once per image.
+Hypotheses are independent through sampling, P3P, scoring, refinement and per-hypothesis gradients; the path has ONE
+exchange in forward -- the softmax / argmax over all scores (esac.cpp:153-155) -- and TWO in backward (the softmax
+normalisation, then the expectation sum_h p_h loss_h every gradient needs, esac.cpp:357-362, esac_derivative.h:372-374);
+SURVEY.md section 8e.  Every rank runs the complete local pipeline on the experts it owns, including the refinement of its
+local best hypothesis (the ranks run concurrently, so that costs no latency), and contributes the record
+    [ scores (M_pad, -inf beyond its own M) | refined pose of its winner (16) | global expert id | local winner | M ]
+to one all-gather; the first strict maximum in rank-major order is the reference's draw() (esac_util.h:519-523).
+
+Two transports:
+  * the library's own NCCL communicator (`init_comm`): esacb200_forward_sharded / esacb200_backward_sharded_nccl issue the
+    collectives on the library's stream, select on the device and synchronise once -- the production path;
+  * torch.distributed (any backend) around esacb200_forward_pack / the exchange callback of esacb200_backward_sharded --
+    kept for the CPU (gloo) tests of the host logic and as a fallback.
+Shards may hold different numbers of hypotheses, including none (real gating draws give every expert a different count).
 """
 from __future__ import annotations
 
 import numpy as np
 
+_NEG_INF = float("-inf")
+_lib_comm: dict = {}   # device index -> (world, rank) of the library communicator
 
-def pack_local(scores, pose16, expert_global: int, local_winner: int):
-    """float64 vector [M_local + 18]."""
+
+def init_comm(group=None, device: int | None = None):
+    """Create the library's NCCL communicator over the ranks of `group` (default: the world group): rank 0 draws an
+    ncclUniqueId, torch.distributed carries its 128 bytes to the others, every rank calls ncclCommInitRank."""
     import torch
-    tail = torch.tensor([float(expert_global), float(local_winner)], dtype=torch.float64, device=scores.device)
-    return torch.cat([scores.reshape(-1), pose16.reshape(16).to(torch.float64), tail])
+    import torch.distributed as dist
+    from . import api
+    if device is None:
+        device = torch.cuda.current_device()
+    world, rank = dist.get_world_size(group), dist.get_rank(group)
+    box = [api.nccl_unique_id() if rank == 0 else None]
+    dist.broadcast_object_list(box, src=dist.get_global_rank(group, 0) if group is not None else 0, group=group)
+    api.context(device).comm_init(world, rank, box[0])
+    _lib_comm[device] = (world, rank)
+    return world, rank
 
 
-def select_global(gathered: np.ndarray, M_local: int):
-    """gathered: [world, M_local + 18].  Returns (global winner index, owning rank, pose 4x4 float32, expert id,
-    probabilities of all hypotheses) with softMax / draw(training=false) semantics (esac_util.h:461-530)."""
+def destroy_comm(device: int | None = None):
+    import torch
+    from . import api
+    if device is None:
+        device = torch.cuda.current_device()
+    if device in _lib_comm:
+        api.context(device).comm_destroy()
+        del _lib_comm[device]
+
+
+def max_over_ranks(value: int, group=None, device=None) -> int:
+    """M_pad: the largest shard size (one small all-reduce; callers with a fixed layout compute it once)."""
+    import torch
+    import torch.distributed as dist
+    t = torch.tensor([int(value)], dtype=torch.int64, device=device)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX, group=group)
+    return max(int(t.item()), 1)
+
+
+def pack_local(scores, pose16, expert_global: int, local_winner: int, M_pad: int | None = None):
+    """float64 record [M_pad + 19] (see the module docstring) from a local result."""
+    import torch
+    scores = scores.reshape(-1).to(torch.float64)
+    M = int(scores.numel())
+    M_pad = M if M_pad is None else int(M_pad)
+    pad = torch.full((M_pad - M,), _NEG_INF, dtype=torch.float64, device=scores.device)
+    if M == 0:
+        tail = torch.tensor([-1.0] * 18 + [0.0], dtype=torch.float64, device=scores.device)
+        return torch.cat([pad, tail])
+    tail = torch.tensor([float(expert_global), float(local_winner), float(M)], dtype=torch.float64, device=scores.device)
+    return torch.cat([scores, pad, pose16.reshape(16).to(torch.float64), tail])
+
+
+def select_global(gathered: np.ndarray, M_pad: int):
+    """gathered: [world, M_pad + 19].  Returns (global winner index = rank * M_pad + local index, owning rank, pose 4x4
+    float32, expert id, probabilities of all M_pad * world slots) with softMax / draw(training=false) semantics
+    (esac_util.h:461-530); padded slots carry -inf and probability 0."""
     world = gathered.shape[0]
-    scores = gathered[:, :M_local].reshape(-1)
-    sf = np.exp(scores - scores.max())
+    scores = gathered[:, :M_pad].reshape(-1)
+    with np.errstate(invalid="ignore"):
+        sf = np.exp(scores - scores.max())
     probs = sf / sf.sum()
     # first strict maximum among p >= EPS (draw(), training=false): argmax returns the first maximum
     winner = int(np.argmax(probs)) if probs.max() >= 1e-8 else 0
-    rank = winner // M_local
+    rank = winner // M_pad
     assert rank < world
-    pose = gathered[rank, M_local:M_local + 16].reshape(4, 4).astype(np.float32)
-    expert = int(gathered[rank, M_local + 16])
+    pose = gathered[rank, M_pad:M_pad + 16].reshape(4, 4).astype(np.float32)
+    expert = int(gathered[rank, M_pad + 16])
     return winner, rank, pose, expert, probs
 
 
@@ -59,52 +113,97 @@ def make_exchange(group=None, device=None):
     return exchange
 
 
-def backward_sharded(coords_local, grads_local, assign_local, gt_pose, w_rot, w_trans, cut, params, hyp_offset: int, group=None):
+def _device_of(t):
+    return t.device.index if getattr(t, "is_cuda", False) else None
+
+
+def backward_sharded(coords_local, grads_local, assign_local, gt_pose, w_rot, w_trans, cut, params, hyp_offset: int, group=None,
+                     device: int | None = None):
     """esac.backward with experts sharded expert-major across ranks: every rank owns its experts' planes and gradient
     slices (no gradient reduction); two KB-sized collectives give every rank the global softmax and the global expected
-    loss, which it returns.  `hyp_offset` = number of hypotheses owned by lower ranks."""
+    loss, which it returns.  `hyp_offset` = number of hypotheses owned by lower ranks.  Uses the library communicator when
+    `init_comm` was called for this device, else torch.distributed through the exchange callback."""
     from . import api
-    dev = coords_local.device if getattr(coords_local, "is_cuda", False) else None
-    ex = make_exchange(group, dev)
+    dev = _device_of(coords_local)
+    if dev is None:
+        dev = device
+    if dev is None:
+        try:
+            import torch
+            dev = torch.cuda.current_device() if torch.cuda.is_available() else None
+        except Exception:
+            dev = None
+    if dev in _lib_comm:
+        return api.backward_sharded_nccl(coords_local, grads_local, assign_local, gt_pose, w_rot, w_trans, cut, *params,
+                                         hyp_offset=hyp_offset, device=dev)
+    if int(assign_local.shape[0]) == 0:
+        # a shard without hypotheses only takes part in the two reductions
+        ex = make_exchange(group, coords_local.device if getattr(coords_local, "is_cuda", False) else None)
+        ex(1, [-1e300, 0.0])
+        return ex(2, [0.0])[0]
+    ex = make_exchange(group, coords_local.device if getattr(coords_local, "is_cuda", False) else None)
     return api.backward_sharded(coords_local, grads_local, assign_local, gt_pose, w_rot, w_trans, cut, *params, exchange=ex,
                                 hyp_offset=hyp_offset)
 
 
 def forward_sharded(coords_local, assign_local, out_pose, params, expert_offset: int, group=None, local_forward=None,
-                    hyp_offset: int = 0):
+                    hyp_offset: int = 0, M_pad: int | None = None, device: int | None = None):
     """esac.forward over experts sharded across the ranks of `group`.  coords_local [E_local,3,H,W] and
-    assign_local [M_local] (expert indices local to the shard) live on this rank; out_pose [4,4] receives the
-    global winner's camera pose on every rank; returns the global expert index."""
+    assign_local [M_local] (expert indices local to the shard; may be empty) live on this rank; out_pose [4,4] receives the
+    global winner's camera pose on every rank; returns the global expert index.  M_pad = the largest M_local of any rank
+    (computed with one extra all-reduce when not given)."""
     import torch
     import torch.distributed as dist
     from . import api
 
     M = int(assign_local.shape[0])
+    dev = _device_of(coords_local)
+    if dev is None:
+        dev = device
+    if dev is None and local_forward is None:
+        dev = torch.cuda.current_device()
+    if local_forward is None and dev in _lib_comm:
+        if M_pad is None:
+            M_pad = max_over_ranks(M, group, torch.device("cuda", dev))
+        return api.forward_sharded(coords_local, assign_local, out_pose, *params, expert_offset=expert_offset, M_pad=M_pad,
+                                   hyp_offset=hyp_offset, device=dev)
+    # ---- torch.distributed transport ----
     if local_forward is None:
         if not hasattr(coords_local, "is_cuda"):
             coords_local, assign_local = torch.from_numpy(coords_local), torch.from_numpy(assign_local)
-        dev = coords_local.device if coords_local.is_cuda else torch.device("cuda", torch.cuda.current_device())
+        tdev = coords_local.device if coords_local.is_cuda else torch.device("cuda", dev)
+        if M_pad is None:
+            M_pad = max_over_ranks(M, group, tdev)
         # host inputs (the reference's callers hold CPU tensors): staged on the current stream, asynchronously if pinned
-        coords_local = coords_local.to(dev, non_blocking=True)
-        assign_local = assign_local.to(dev, non_blocking=True)
-        ctx = api.context(dev.index)
+        coords_local = coords_local.to(tdev, non_blocking=True)
+        assign_local = assign_local.to(tdev, non_blocking=True)
+        ctx = api.context(tdev.index)
         ctx.set_option("hyp_offset", hyp_offset)
-        buf = torch.empty(M + 18, dtype=torch.float64, device=dev)
+        buf = torch.empty(M_pad + 19, dtype=torch.float64, device=tdev)
         try:
-            api.forward_pack(coords_local, assign_local, params, expert_offset, buf)   # enqueued, no host sync
+            if M > 0:
+                api.forward_pack(coords_local, assign_local, params, expert_offset, buf, M_pad=M_pad)   # enqueued, no host sync
+            else:
+                buf.copy_(pack_local(torch.empty(0, dtype=torch.float64, device=tdev), None, -1, 0, M_pad))
         finally:
             ctx.set_option("hyp_offset", 0)
     else:
-        scores, pose, e_local, lw = local_forward(coords_local, assign_local, params)
-        buf = pack_local(scores, pose, expert_offset + e_local, lw)
+        if M_pad is None:
+            M_pad = max_over_ranks(M, group, None)
+        if M > 0:
+            scores, pose, e_local, lw = local_forward(coords_local, assign_local, params)
+            buf = pack_local(scores, pose, expert_offset + e_local, lw, M_pad)
+        else:
+            buf = pack_local(torch.empty(0, dtype=torch.float64), None, -1, 0, M_pad)
     world = dist.get_world_size(group)
-    gathered = torch.empty(world * (M + 18), dtype=torch.float64, device=buf.device)
+    rec = M_pad + 19
+    gathered = torch.empty(world * rec, dtype=torch.float64, device=buf.device)
     dist.all_gather_into_tensor(gathered, buf, group=group)
-    g = gathered.view(world, M + 18)
+    g = gathered.view(world, rec)
     if g.is_cuda:
         # selection on the device: first maximum = draw(training=false); ONE 17-value read-back (the only host sync of the step)
-        w = torch.argmax(g[:, :M].reshape(-1))
-        tail = g.reshape(-1)[(w // M) * (M + 18) + M + torch.arange(17, device=g.device)]
+        w = torch.argmax(g[:, :M_pad].reshape(-1))
+        tail = g.reshape(-1)[(w // M_pad) * rec + M_pad + torch.arange(17, device=g.device)]
         if hasattr(out_pose, "is_cuda") and out_pose.is_cuda:
             out_pose.copy_(tail[:16].reshape(4, 4))
             expert = int(tail[16].item())
@@ -116,7 +215,7 @@ def forward_sharded(coords_local, assign_local, out_pose, params, expert_offset:
         if expert < 0:
             raise RuntimeError("hypAssignment holds an expert index outside the shard's experts")
     else:
-        _, _, gpose, expert, _ = select_global(g.numpy(), M)
+        _, _, gpose, expert, _ = select_global(g.numpy(), M_pad)
     if hasattr(out_pose, "copy_"):
         out_pose.copy_(torch.from_numpy(gpose))
     else:

@@ -92,16 +92,43 @@ int esacb200_backward_sharded(esacb200_ctx* ctx, const float* coords, float* gra
 
 /* The local half of a sharded esac_forward, enqueued WITHOUT a host synchronisation: runs sample -> score -> select ->
  * refine on this shard's experts / hypotheses and writes the record the shards exchange,
- *   pack_out[0..M)   soft-inlier scores (esac.cpp:147-150),      pack_out[M..M+16)  camera pose of the local winner,
- *   pack_out[M+16]   expert_offset + its expert (or -1 if hypAssignment held an index outside [0,E)),
- *   pack_out[M+17]   its local hypothesis index,
+ *   pack_out[0..M_pad)      soft-inlier scores (esac.cpp:147-150); entries >= M are -inf (shards may hold different numbers
+ *                           of hypotheses, the records of a collective must have one size: M_pad = the largest M),
+ *   pack_out[M_pad..+16)    camera pose of the local winner,
+ *   pack_out[M_pad+16]      expert_offset + its expert (or -1 if hypAssignment held an index outside [0,E)),
+ *   pack_out[M_pad+17]      its local hypothesis index,        pack_out[M_pad+18]  M,
  * as doubles into DEVICE memory, stream-ordered on the context's stream.  coords / assign must be device pointers (a host
- * buffer would force the synchronisation this entry exists to avoid).  esac_b200/sharded.py all-gathers the records and
- * applies softMax / draw (esac_util.h:461-530) to the concatenated scores. */
+ * buffer would force the synchronisation this entry exists to avoid).  M may be 0 (coords / assign are then ignored). */
 int esacb200_forward_pack(esacb200_ctx* ctx, const float* coords, int E, int H, int W, const int64_t* assign,
-                          int64_t assign_stride, int M, int shiftX, int shiftY, float focalLength, float ppointX,
+                          int64_t assign_stride, int M, int M_pad, int shiftX, int shiftY, float focalLength, float ppointX,
                           float ppointY, float inlierThreshold, float inlierAlpha, float inlierBeta, float maxReproj,
                           int subSampling, int expert_offset, double* pack_out);
+
+/* ---- sharded entry points over NCCL (one process per GPU) ------------------------------------------------------------
+ * The path has ONE exchange in forward (scores -> softMax / draw, esac.cpp:153-155) and TWO in backward (softmax
+ * normalisation; the expectation sum_h p_h loss_h, esac.cpp:357-362, esac_derivative.h:372-374); SURVEY.md 8e.  The library
+ * issues them itself as NCCL collectives on the context's stream.  NCCL is resolved at run time (dlopen of libnccl.so.2, the
+ * copy the process already holds if any), so the library still loads where NCCL is absent.
+ * esacb200_nccl_unique_id: 128-byte ncclUniqueId (rank 0 creates it, the caller distributes it by any means).
+ * esacb200_comm_init:     ncclCommInitRank on the context's device; collective over all ranks. */
+int esacb200_nccl_unique_id(void* out128);
+int esacb200_comm_init(esacb200_ctx* ctx, int world, int rank, const void* id128);
+int esacb200_comm_destroy(esacb200_ctx* ctx);
+/* esac_forward over all shards: local pipeline -> record -> one ncclAllGather -> softMax / draw over the records on the device
+ * (first strict maximum in rank-major order) -> one 80-byte read-back.  Every rank receives the global winner's camera pose
+ * and (global) expert index.  coords / assign host or device pointers; M may be 0; M_pad = max M over the ranks. */
+int esacb200_forward_sharded(esacb200_ctx* ctx, const float* coords, int E, int H, int W, const int64_t* assign,
+                             int64_t assign_stride, int M, int M_pad, float* out_pose, int shiftX, int shiftY, float focalLength,
+                             float ppointX, float ppointY, float inlierThreshold, float inlierAlpha, float inlierBeta,
+                             float maxReproj, int subSampling, int expert_offset, int* out_expert);
+/* esac_backward over all shards (gradient slices are disjoint when experts are dealt expert-major: no gradient collective):
+ * all-gather of (max score, sum exp) -> global probabilities; all-reduce of the partial expectations -> *out_loss = the
+ * global expected loss on every rank.  Option "hyp_offset" as for esacb200_backward_sharded.  M may be 0. */
+int esacb200_backward_sharded_nccl(esacb200_ctx* ctx, const float* coords, float* grads, int E, int H, int W,
+                                   const int64_t* assign, int64_t assign_stride, int M, const float* gt_pose, float wLossRot,
+                                   float wLossTrans, float lossCut, int shiftX, int shiftY, float focalLength, float ppointX,
+                                   float ppointY, float inlierThreshold, float inlierAlpha, float inlierBeta, float maxReproj,
+                                   int subSampling, double* out_loss);
 
 /* esac_forward over B images of one shape (the reference's callers loop with batch_size=1, test_esac.py:137):
  * coords float32 [B,E,3,H,W], assign int64 [B,M] (rows contiguous, element stride assign_stride; 0 = one expert for all),

@@ -21,6 +21,14 @@ def _free_port():
     return p
 
 
+def _split(E, world):
+    """Experts dealt expert-major, as evenly as possible (E need not be divisible by the number of ranks)."""
+    base, extra = divmod(E, world)
+    sizes = [base + (1 if r < extra else 0) for r in range(world)]
+    starts = [sum(sizes[:r]) for r in range(world)]
+    return starts, sizes
+
+
 def _worker(rank, world, port, q):
     import torch.distributed as dist
     os.environ["MASTER_ADDR"] = "127.0.0.1"
@@ -29,26 +37,58 @@ def _worker(rank, world, port, q):
     dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
     import esac_b200.api as api
     from esac_b200 import sharded
-    E, Mper = 4, 24
+    E, Mper = 5, 24                      # 5 experts over 2 ranks: 3 + 2 -> shards of 72 and 48 hypotheses
     sc = make_scene(E=E, H=30, W=40, M=Mper, sub=8, seed=77, per_expert=True, active_only=False)
-    Eloc = E // world
-    e0 = rank * Eloc
+    starts, sizes = _split(E, world)
+    e0, Eloc = starts[rank], sizes[rank]
     hsel = slice(e0 * Mper, (e0 + Eloc) * Mper)
+    M_pad = max(sizes) * Mper
     dev = torch.device("cuda", rank)
     coords_l = torch.from_numpy(sc.coords[e0:e0 + Eloc]).to(dev)
     assign_l = torch.from_numpy(sc.assign[hsel] - e0).to(dev)
     ctx = api.context(rank)
     ctx.set_option("fixed_seed", 1)
-    # ---- forward ----
+    res = {"rank": rank}
+    # ---- transport 1: torch.distributed around forward_pack / the exchange callback ----
     ctx.set_seed(5)
     out = torch.zeros(4, 4, device=dev)
-    e = sharded.forward_sharded(coords_l, assign_l, out, sc.params, expert_offset=e0, hyp_offset=e0 * Mper)
-    # ---- backward ----
+    res["expert_t"] = sharded.forward_sharded(coords_l, assign_l, out, sc.params, expert_offset=e0, hyp_offset=e0 * Mper, M_pad=M_pad)
+    res["pose_t"] = out.cpu().numpy()
     ctx.set_seed(5)
     grads_l = torch.zeros_like(coords_l)
-    loss = sharded.backward_sharded(coords_l, grads_l, assign_l, torch.from_numpy(sc.gt_pose), 1.0, 100.0, 100.0, sc.params,
-                                    hyp_offset=e0 * Mper)
-    res = {"rank": rank, "expert": e, "pose": out.cpu().numpy(), "loss": loss, "grads": grads_l.cpu().numpy()}
+    res["loss_t"] = sharded.backward_sharded(coords_l, grads_l, assign_l, torch.from_numpy(sc.gt_pose), 1.0, 100.0, 100.0, sc.params,
+                                             hyp_offset=e0 * Mper)
+    res["grads_t"] = grads_l.cpu().numpy()
+    # ---- transport 2: the library's own NCCL communicator ----
+    sharded.init_comm(device=rank)
+    ctx.set_seed(5)
+    out2 = torch.zeros(4, 4, device=dev)
+    res["expert"] = sharded.forward_sharded(coords_l, assign_l, out2, sc.params, expert_offset=e0, hyp_offset=e0 * Mper, M_pad=M_pad)
+    res["pose"] = out2.cpu().numpy()
+    # host tensors through the same entry (what the reference's callers hold)
+    ctx.set_seed(5)
+    out3 = torch.zeros(4, 4)
+    res["expert_h"] = sharded.forward_sharded(coords_l.cpu(), assign_l.cpu(), out3, sc.params, expert_offset=e0,
+                                              hyp_offset=e0 * Mper, M_pad=M_pad, device=rank)
+    res["pose_h"] = out3.numpy()
+    ctx.set_seed(5)
+    grads2 = torch.zeros_like(coords_l)
+    res["loss"] = sharded.backward_sharded(coords_l, grads2, assign_l, torch.from_numpy(sc.gt_pose), 1.0, 100.0, 100.0, sc.params,
+                                           hyp_offset=e0 * Mper)
+    res["grads"] = grads2.cpu().numpy()
+    # ---- a rank WITHOUT hypotheses (rank 1 hands everything to rank 0's experts): must still take part ----
+    ctx.set_seed(5)
+    if rank == 0:
+        c_e, a_e = torch.from_numpy(sc.coords).to(dev), torch.from_numpy(sc.assign).to(dev)
+    else:
+        c_e, a_e = torch.zeros(1, 3, 30, 40, device=dev), torch.zeros(0, dtype=torch.int64, device=dev)
+    out4 = torch.zeros(4, 4, device=dev)
+    res["expert_e"] = sharded.forward_sharded(c_e, a_e, out4, sc.params, expert_offset=0, hyp_offset=0, M_pad=E * Mper)
+    res["pose_e"] = out4.cpu().numpy()
+    ctx.set_seed(5)
+    g_e = torch.zeros_like(c_e)
+    res["loss_e"] = sharded.backward_sharded(c_e, g_e, a_e, torch.from_numpy(sc.gt_pose), 1.0, 100.0, 100.0, sc.params, hyp_offset=0)
+    sharded.destroy_comm(rank)
     if rank == 0:  # the unsharded problem on one GPU
         ctx.set_seed(5)
         ref_out = np.zeros((4, 4), np.float32)
@@ -56,7 +96,7 @@ def _worker(rank, world, port, q):
         ctx.set_seed(5)
         g = np.zeros_like(sc.coords)
         ref_loss = api.backward(sc.coords, g, sc.assign, sc.gt_pose, 1.0, 100.0, 100.0, *sc.params)
-        res.update(ref_expert=ref_e, ref_pose=ref_out, ref_loss=ref_loss, ref_grads=g)
+        res.update(ref_expert=ref_e, ref_pose=ref_out, ref_loss=ref_loss, ref_grads=g, starts=starts, sizes=sizes)
     q.put(res)
     dist.barrier()
     dist.destroy_process_group()
@@ -79,13 +119,16 @@ def test_two_gpu_sharding_reproduces_single_gpu():
         p.join(timeout=120)
         assert p.exitcode == 0
     ref = res[0]
+    scale = max(np.abs(ref["ref_grads"]).max(), 1e-12)
     for r in (0, 1):
-        assert res[r]["expert"] == ref["ref_expert"]
-        assert np.allclose(res[r]["pose"], ref["ref_pose"], atol=1e-6)
-        assert abs(res[r]["loss"] - ref["ref_loss"]) < 1e-9 * max(1.0, abs(ref["ref_loss"]))
-        sl = slice(2 * r, 2 * r + 2)
-        scale = max(np.abs(ref["ref_grads"]).max(), 1e-12)
-        assert np.abs(res[r]["grads"] - ref["ref_grads"][sl]).max() / scale < 1e-6
+        sl = slice(ref["starts"][r], ref["starts"][r] + ref["sizes"][r])
+        for tag in ("_t", "", "_h", "_e"):          # torch transport, library NCCL, host tensors, empty shard on rank 1
+            assert res[r]["expert" + tag] == ref["ref_expert"], tag
+            assert np.allclose(res[r]["pose" + tag], ref["ref_pose"], atol=1e-6), tag
+        for tag in ("_t", "", "_e"):
+            assert abs(res[r]["loss" + tag] - ref["ref_loss"]) < 1e-9 * max(1.0, abs(ref["ref_loss"])), tag
+        for tag in ("_t", ""):
+            assert np.abs(res[r]["grads" + tag] - ref["ref_grads"][sl]).max() / scale < 1e-6, tag
     assert np.abs(ref["ref_grads"]).max() > 0
 
 

@@ -13,7 +13,7 @@ from esac_b200 import sharded
 
 def test_select_global_is_first_strict_maximum():
     M = 5
-    g = np.zeros((3, M + 18))
+    g = np.zeros((3, M + 19))
     g[0, :M] = [1, 2, 3, 2, 1]
     g[1, :M] = [3, 9, 9, 0, 0]       # tie inside rank 1: the first one wins
     g[2, :M] = [9, 0, 0, 0, 0]       # tie across ranks: the lower global index wins
@@ -33,11 +33,11 @@ def _free_port():
     return p
 
 
-def _worker(rank, world, port, q):
+def _worker(rank, world, port, q, unequal=False):
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
     dist.init_process_group("gloo", rank=rank, world_size=world)
-    M = 6
+    M = (9 if rank == 1 else 0) if unequal else 6   # unequal: rank 0 holds NO hypotheses, rank 1 nine
     rng = np.random.default_rng(rank)
     scores = torch.from_numpy(rng.uniform(0, 50, M))
     if rank == 1:
@@ -70,6 +70,35 @@ def test_forward_sharded_world2_gloo():
     for rank, e, pose in res:
         assert e == 1 * 3 + 2          # rank 1's shard, local expert 2
         assert np.allclose(pose, np.eye(4) * 2)
+
+
+def test_forward_sharded_unequal_and_empty_shards_gloo():
+    """Real gating draws give every expert shard a different hypothesis count, possibly zero: records are padded to the
+    largest shard with -inf scores and an empty shard contributes an all -inf record."""
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    ps = [ctx.Process(target=_worker, args=(r, 2, port, q, True)) for r in range(2)]
+    for p in ps:
+        p.start()
+    for p in ps:
+        p.join(timeout=240)
+        assert p.exitcode == 0
+    for rank, e, pose in [q.get(timeout=5) for _ in range(2)]:
+        assert e == 1 * 3 + 2
+        assert np.allclose(pose, np.eye(4) * 2)
+
+
+def test_select_global_ignores_padding():
+    M_pad = 4
+    g = np.full((2, M_pad + 19), -1.0)
+    g[0, :M_pad] = [5.0, -np.inf, -np.inf, -np.inf]      # rank 0 holds one hypothesis
+    g[1, :M_pad] = [1.0, 9.0, 9.0, 2.0]
+    g[1, M_pad:M_pad + 16] = np.eye(4).reshape(-1) * 3
+    g[1, M_pad + 16] = 7
+    w, rank, pose, expert, probs = sharded.select_global(g, M_pad)
+    assert (w, rank, expert) == (M_pad + 1, 1, 7) and pose[0, 0] == 3.0
+    assert probs[1] == 0.0 and abs(probs.sum() - 1) < 1e-12
 
 
 def _exchange_worker(rank, world, port, q):
