@@ -180,8 +180,8 @@ def split_experts(E: int, world: int):
 def run_configs(rank: int, world: int, dev, api, sharded, dist, reps: int = 4):
     """c3: 19 experts, 256 hypotheses per image, batch of 8 images -- images dealt to the ranks (no communication);
     c4: 10 experts x 512 hypotheses each, ONE image -- strong scaling, experts dealt expert-major (unequal shards);
-    c5: 20 experts, 1024 hypotheses, forward + backward (the esac_loss of train_esac.py:105-183) -- experts dealt expert-major,
-        the two backward exchanges as NCCL collectives inside the library.
+    c5: 20 experts, 1024 hypotheses, forward + backward (the esac_loss of train_esac.py:105-183) -- hypotheses dealt to the ranks,
+        all planes everywhere; the two backward exchanges and the gradient sum as NCCL collectives inside the library.
     Every entry: whole-job hypotheses/s = hypotheses of the job / max-over-ranks device time."""
     import torch
     from esac_b200.synth import make_scene
@@ -241,32 +241,33 @@ def run_configs(rank: int, world: int, dev, api, sharded, dist, reps: int = 4):
     sc = make_scene(E=E5, H=H, W=W, M=M5, sub=SUB, seed=500, active_only=False)   # 1024 hypotheses drawn from the gating (60% on the true expert)
     order = np.argsort(sc.assign, kind="stable")                                    # hypotheses grouped expert-major
     assign_sorted = sc.assign[order]
-    starts, sizes = split_experts(E5, world)
-    e0, El = starts[rank], sizes[rank]
-    sel = (assign_sorted >= e0) & (assign_sorted < e0 + El)
-    hyp_off = int(np.searchsorted(assign_sorted, e0))
-    counts = [int(((assign_sorted >= s) & (assign_sorted < s + z)).sum()) for s, z in zip(starts, sizes)]
+    # hypothesis-major: every rank holds all 20 planes (74 MB) and every N-th of the expert-sorted hypotheses, so the
+    # contributing hypotheses -- all on the true expert -- spread over the ranks; their gradient slices overlap and are summed
+    # with one ncclAllReduce (esacb200_backward_sharded_nccl, reduce_grads)
+    counts = [len(range(r, M5, world)) for r in range(world)]   # dealt round-robin: hypothesis h of the sorted list goes to rank h % N
     M_pad = max(max(counts), 1)
-    c_l = torch.from_numpy(sc.coords[e0:e0 + El]).to(dev)
-    a_l = torch.from_numpy(assign_sorted[sel] - e0).to(dev)
+    c_l = torch.from_numpy(sc.coords).to(dev)
+    a_l = torch.from_numpy(np.ascontiguousarray(assign_sorted[rank::world])).to(dev)
     g_l = torch.zeros_like(c_l)
     gt = torch.from_numpy(sc.gt_pose)
     if world == 1:
         f_fwd = lambda: api.forward(c_l, a_l, pose, *sc.params)
         f_bwd = lambda: api.backward(c_l, g_l, a_l, gt, 1.0, 100.0, 100.0, *sc.params)
     else:
-        f_fwd = lambda: sharded.forward_sharded(c_l, a_l, pose, sc.params, expert_offset=e0, hyp_offset=hyp_off, M_pad=M_pad)
-        f_bwd = lambda: sharded.backward_sharded(c_l, g_l, a_l, gt, 1.0, 100.0, 100.0, sc.params, hyp_offset=hyp_off)
+        f_fwd = lambda: sharded.forward_sharded(c_l, a_l, pose, sc.params, expert_offset=0, hyp_offset=rank, hyp_stride=world, M_pad=M_pad)
+        f_bwd = lambda: sharded.backward_sharded(c_l, g_l, a_l, gt, 1.0, 100.0, 100.0, sc.params, hyp_offset=rank, hyp_stride=world,
+                                                 reduce_grads=True)
     ms_f = timed(f_fwd, reps)
     ms_b = timed(f_bwd, reps)
     st = api.context(dev.index).stats()
     out["c5_20experts_1024hyp_forward_backward"] = {
         "value": M5 / ((ms_f + ms_b) * 1e-3), "unit": UNIT, "ms_forward": ms_f, "ms_backward": ms_b, "hyps_per_image": M5,
         "hyps_per_rank": counts, "contributing_hypotheses_rank0": st["n_contrib"], "scaling": "strong",
-        "parallelism": "single GPU" if world == 1 else "expert-major shard; forward: 1 ncclAllGather; backward: ncclAllGather of "
-                       "(max, sum exp) + ncclAllReduce of the expectation, gradient slices disjoint",
-        "note": "the gating puts 60% of the hypotheses and all contributing ones on the true expert's rank: the refinement of the "
-                "contributing hypotheses does not shard"}
+        "parallelism": "single GPU" if world == 1 else "hypothesis-major shard (all planes on every rank, hypotheses dealt round-robin); forward: "
+                       "1 ncclAllGather; backward: ncclAllGather of (max, sum exp) + ncclAllReduce of the expectation + "
+                       "ncclAllReduce of the 74 MB gradient tensor",
+        "note": "the gating puts 60% of the hypotheses and every contributing one on the true expert: dealing experts to ranks "
+                "would leave the refine-all stage on one GPU, dealing hypotheses spreads it"}
     return out
 
 

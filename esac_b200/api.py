@@ -34,6 +34,7 @@ class Stats(C.Structure):
 
 
 _lib = None
+PACK_TAIL = 21  # doubles behind the M_pad scores of a shard's record (include/esac_b200.h)
 EXCHANGE_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_int, C.POINTER(C.c_double), C.c_int)
 
 
@@ -72,7 +73,7 @@ def load_library() -> C.CDLL:
     lib.esacb200_comm_destroy.restype = i32
     lib.esacb200_forward_sharded.argtypes = [vp, vp, i32, i32, i32, vp, i64, i32, i32, vp] + cam + [i32, C.POINTER(i32)]
     lib.esacb200_forward_sharded.restype = i32
-    lib.esacb200_backward_sharded_nccl.argtypes = [vp, vp, vp, i32, i32, i32, vp, i64, i32, vp, f32, f32, f32] + cam + [C.POINTER(f64)]
+    lib.esacb200_backward_sharded_nccl.argtypes = [vp, vp, vp, i32, i32, i32, vp, i64, i32, vp, f32, f32, f32] + cam + [i32, C.POINTER(f64)]
     lib.esacb200_backward_sharded_nccl.restype = i32
     lib.esacb200_backward_batch.argtypes = ([vp, i32, vp, vp, i32, i32, i32, vp, i64, i32, vp, f32, f32, f32, vp, vp] + cam[2:] +
                                              [vp])
@@ -587,7 +588,7 @@ def nccl_unique_id() -> bytes:
 def forward_pack(sceneCoordinates, hypAssignment, params, expert_offset: int, pack_out, M_pad: int | None = None):
     """The local half of a sharded forward, enqueued on the current CUDA stream without a host synchronisation
     (esacb200_forward_pack).  sceneCoordinates [E,3,H,W] / hypAssignment [M] are CUDA tensors, params the positional tail of
-    esac.forward (shiftX .. subSampling), pack_out a CUDA float64 tensor of M_pad + 19 elements (see include/esac_b200.h);
+    esac.forward (shiftX .. subSampling), pack_out a CUDA float64 tensor of M_pad + 21 elements (see include/esac_b200.h);
     M_pad (default M) = the largest M of any shard."""
     _check(sceneCoordinates, "Float", 4, "sceneCoordinates")
     _check(hypAssignment, "Long", 1, "hypAssignment")
@@ -596,8 +597,8 @@ def forward_pack(sceneCoordinates, hypAssignment, params, expert_offset: int, pa
     co = _Arg(sceneCoordinates)
     aptr, astride, M, adev, _keep = _assign_arg(hypAssignment)
     M_pad = M if M_pad is None else int(M_pad)
-    if pack_out.dtype != __import__("torch").float64 or pack_out.numel() != M_pad + 19 or not pack_out.is_contiguous():
-        raise RuntimeError("pack_out must be a contiguous float64 tensor of M_pad + 19 elements")
+    if pack_out.dtype != __import__("torch").float64 or pack_out.numel() != M_pad + PACK_TAIL or not pack_out.is_contiguous():
+        raise RuntimeError(f"pack_out must be a contiguous float64 tensor of M_pad + {PACK_TAIL} elements")
     ctx = _pick_ctx(co.device, adev, pack_out.device.index)
     E, _, H, W = (int(v) for v in sceneCoordinates.shape)
     shiftX, shiftY, f, ppx, ppy, tau, alpha, beta, maxReproj, sub = params
@@ -608,7 +609,7 @@ def forward_pack(sceneCoordinates, hypAssignment, params, expert_offset: int, pa
 
 def forward_sharded(sceneCoordinates, hypAssignment, outPose, shiftX, shiftY, focalLength, ppointX, ppointY, inlierThreshold,
                     inlierAlpha, inlierBeta, maxReproj, subSampling, expert_offset: int = 0, M_pad: int | None = None,
-                    hyp_offset: int = 0, device: int | None = None) -> int:
+                    hyp_offset: int = 0, device: int | None = None, hyp_stride: int = 1) -> int:
     """esac.forward over experts / hypotheses sharded across the ranks of the library's communicator (Context.comm_init):
     this rank's shard in, the GLOBAL winner's pose (outPose, in place) and expert index out, on every rank.  One
     ncclAllGather on the library's stream, no torch collective.  hypAssignment may be empty (M = 0)."""
@@ -624,6 +625,7 @@ def forward_sharded(sceneCoordinates, hypAssignment, outPose, shiftX, shiftY, fo
     E, _, H, W = (int(s) for s in sceneCoordinates.shape)
     expert = C.c_int(-1)
     ctx.set_option("hyp_offset", hyp_offset)
+    ctx.set_option("hyp_stride", hyp_stride)
     try:
         rc = ctx.lib.esacb200_forward_sharded(ctx.handle, co.ptr, E, H, W, aptr, astride, M, M_pad, op.ptr, int(shiftX), int(shiftY),
                                               float(focalLength), float(ppointX), float(ppointY), float(inlierThreshold),
@@ -631,6 +633,7 @@ def forward_sharded(sceneCoordinates, hypAssignment, outPose, shiftX, shiftY, fo
                                               int(expert_offset), C.byref(expert))
     finally:
         ctx.set_option("hyp_offset", 0)
+        ctx.set_option("hyp_stride", 1)
     ctx.check(rc)
     op.finish()
     return int(expert.value)
@@ -638,9 +641,10 @@ def forward_sharded(sceneCoordinates, hypAssignment, outPose, shiftX, shiftY, fo
 
 def backward_sharded_nccl(sceneCoordinates, outGradients, hypAssignment, gtPose, wLossRot, wLossTrans, lossCut, shiftX, shiftY,
                           focalLength, ppointX, ppointY, inlierThreshold, inlierAlpha, inlierBeta, maxReproj, subSampling,
-                          hyp_offset: int = 0, device: int | None = None) -> float:
+                          hyp_offset: int = 0, device: int | None = None, reduce_grads: bool = False, hyp_stride: int = 1) -> float:
     """esac.backward on this rank's shard; the two exchanges run as NCCL collectives inside the library.  Returns the GLOBAL
-    expected loss; outGradients receives this shard's gradient slices.  hypAssignment may be empty."""
+    expected loss; outGradients receives this shard's gradient slices, or -- reduce_grads, hypothesis-major sharding with all
+    planes on every rank -- the gradient summed over all ranks.  hypAssignment may be empty."""
     _check(sceneCoordinates, "Float", 4, "sceneCoordinates")
     _check(outGradients, "Float", 4, "outGradients")
     _check(hypAssignment, "Long", 1, "hypAssignment")
@@ -654,17 +658,19 @@ def backward_sharded_nccl(sceneCoordinates, outGradients, hypAssignment, gtPose,
     E, _, H, W = (int(s) for s in sceneCoordinates.shape)
     loss = C.c_double(0.0)
     ctx.set_option("hyp_offset", hyp_offset)
+    ctx.set_option("hyp_stride", hyp_stride)
     try:
         rc = ctx.lib.esacb200_backward_sharded_nccl(ctx.handle, co.ptr, gr.ptr, E, H, W, aptr, astride, M, gt.ptr, float(wLossRot),
                                                     float(wLossTrans), float(lossCut), int(shiftX), int(shiftY), float(focalLength),
                                                     float(ppointX), float(ppointY), float(inlierThreshold), float(inlierAlpha),
-                                                    float(inlierBeta), float(maxReproj), int(subSampling), C.byref(loss))
+                                                    float(inlierBeta), float(maxReproj), int(subSampling), int(bool(reduce_grads)),
+                                                    C.byref(loss))
     finally:
         ctx.set_option("hyp_offset", 0)
+        ctx.set_option("hyp_stride", 1)
     ctx.check(rc)
     gr.finish()
     return float(loss.value)
-
 
 
 def score_poses(sceneCoordinates, hypAssignment, poses6, shiftX, shiftY, focalLength, ppointX, ppointY,

@@ -440,4 +440,25 @@ void launch_backward(const BwdArgs& a, int max_jobs, cudaStream_t st) {
     bwd_assemble_kernel<<<ga, kBwdThreads, 0, st>>>(a, x);
 }
 
+// dst += src (the rank-summed gradient of a hypothesis-major sharded backward joins the caller's tensor: esac.cpp:501-506 is +=)
+__global__ void add_inplace_kernel(float* __restrict__ dst, const float* __restrict__ src, size_t n) {
+    const size_t n4 = n / 4;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (size_t)gridDim.x * blockDim.x) {
+        float4 a = reinterpret_cast<float4*>(dst)[i];
+        const float4 b = reinterpret_cast<const float4*>(src)[i];
+        a.x += b.x; a.y += b.y; a.z += b.z; a.w += b.w;
+        reinterpret_cast<float4*>(dst)[i] = a;
+    }
+    for (size_t i = n4 * 4 + (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) dst[i] += src[i];
+}
+
+__global__ void add_inplace_scalar_kernel(float* __restrict__ dst, const float* __restrict__ src, size_t n) {
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) dst[i] += src[i];
+}
+
+void launch_add_inplace(float* dst, const float* src, size_t n, cudaStream_t st) {
+    if ((((uintptr_t)dst) | ((uintptr_t)src)) & 15) add_inplace_scalar_kernel<<<1184, 256, 0, st>>>(dst, src, n);  // unaligned views
+    else add_inplace_kernel<<<1184, 256, 0, st>>>(dst, src, n);
+}
+
 }  // namespace esacb200

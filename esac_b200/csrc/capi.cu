@@ -73,7 +73,7 @@ struct esacb200_ctx {
     int refine_profile = 0;    // 1: block 0 of the refinement kernel records phase cycle counts (esacb200_get_refine_profile)
     int refine_jobs_per_group = 3;
     int sample_prefilter = 1;
-    int hyp_offset = 0;
+    int hyp_offset = 0, hyp_stride = 1;
     int score_ppt_opt = 0, score_hc_opt = 0;
     int refine_coresident = 0;
     char err[512] = {0};
@@ -93,7 +93,7 @@ struct esacb200_ctx {
     // NCCL communicator of the sharded entry points (esacb200_comm_init); the library is resolved at run time with dlopen
     void* nccl_comm = nullptr;
     int comm_world = 1, comm_rank = 0;
-    DevBuf gathered;
+    DevBuf gathered, grads_work;
     std::vector<esacb200_ctx*> workers;  // lazily created contexts of esacb200_backward_batch (own stream + workspace each)
 };
 
@@ -128,6 +128,7 @@ struct NcclApi {
     const char* (*GetErrorString)(int) = nullptr;
     bool ok = false;
 };
+constexpr int kNcclFloat32 = 7;  // ncclFloat
 constexpr int kNcclFloat64 = 8;  // ncclDouble
 constexpr int kNcclSum = 0;      // ncclSum
 
@@ -352,7 +353,7 @@ int run_sample(esacb200_ctx* ctx, const Plan& pl, uint64_t seed) {
     CK(ctx->coords4.ensure((size_t)P.E * P.N * sizeof(float4)));
     ctx->st.kernel_launches += launch_sample(pl.d_coords, ctx->coords4.as<float4>(), ctx->assign32.as<int>(), P, seed, ctx->max_tries,
                                              ctx->inj_M ? ctx->inject.as<int>() : nullptr, ctx->inj_T, st, G, ctx->sm_count,
-                                             ctx->sample_prefilter, ctx->hyp_offset, ctx->poses.as<Pose>(), ctx->cells.as<int>(),
+                                             ctx->sample_prefilter, ctx->hyp_offset, ctx->hyp_stride, ctx->poses.as<Pose>(), ctx->cells.as<int>(),
                                              ctx->tries.as<int>(), ctx->stream, ctx->aux_stream, ctx->ev_fork, ctx->ev_join,
                                              pl.split_e, ctx->perm.as<int>(), ctx->offsets.as<int>(), ctx->ev_copied);
     CK(cudaGetLastError());
@@ -579,7 +580,7 @@ void esacb200_destroy(esacb200_ctx* ctx) {
                       &ctx->slot_of, &ctx->chunks, &ctx->scalars, &ctx->centres, &ctx->poses, &ctx->poses_ref, &ctx->cells,
                       &ctx->tries, &ctx->posepk, &ctx->part, &ctx->scores, &ctx->probs, &ctx->stats, &ctx->contrib,
                       &ctx->masks, &ctx->rounds, &ctx->scratch, &ctx->barrier, &ctx->out17, &ctx->inject, &ctx->losses,
-                      &ctx->red, &ctx->hypgrad, &ctx->job_of, &ctx->gt, &ctx->smp_int, &ctx->smp_surv, &ctx->coords4, &ctx->coords_alt, &ctx->assign64_alt, &ctx->out_batch, &ctx->prof, &ctx->gathered};
+                      &ctx->red, &ctx->hypgrad, &ctx->job_of, &ctx->gt, &ctx->smp_int, &ctx->smp_surv, &ctx->coords4, &ctx->coords_alt, &ctx->assign64_alt, &ctx->out_batch, &ctx->prof, &ctx->gathered, &ctx->grads_work};
     for (DevBuf* b : bufs) b->release();
     for (int i = 0; i < EV_COUNT; ++i)
         if (ctx->ev[i]) cudaEventDestroy(ctx->ev[i]);
@@ -624,6 +625,7 @@ int esacb200_set_option(esacb200_ctx* ctx, const char* key, double v) {
     else if (!strcmp(key, "upload_split")) ctx->upload_split = v != 0;  // host maps in two halves, sampling under the second copy
     else if (!strcmp(key, "sample_groups")) ctx->sample_groups = v >= 2 ? 2 : 1;  // 2: two interleaved lanes on two streams
     else if (!strcmp(key, "hyp_offset")) ctx->hyp_offset = (int)v;  // global index of local hypothesis 0 (sharded runs)
+    else if (!strcmp(key, "hyp_stride")) ctx->hyp_stride = v < 1 ? 1 : (int)v;  // ... of local hypothesis h: offset + h * stride
     else if (!strcmp(key, "score_ppt")) ctx->score_ppt_opt = (int)v;   // 0 = automatic, else 2 / 4 / 8 cells per thread
     else if (!strcmp(key, "score_hc")) ctx->score_hc_opt = (int)v;     // 0 = automatic, else hypotheses per chunk (<= 64)
     else if (!strcmp(key, "batch_workers")) ctx->batch_workers = v < 1 ? 1 : (v > 16 ? 16 : (int)v);  // streams of backward_batch
@@ -715,7 +717,8 @@ static int enqueue_forward_record(esacb200_ctx* ctx, const float* coords, int E,
         CK(ctx->scores.ensure(8));
         CK(ctx->out17.ensure(32 * 4));
     }
-    launch_pack_forward(ctx->scores.as<double>(), ctx->out17.as<float>(), M, M_pad, expert_offset, pack_out, ctx->stream);
+    launch_pack_forward(ctx->scores.as<double>(), ctx->out17.as<float>(), M, M_pad, expert_offset, ctx->hyp_offset, ctx->hyp_stride,
+                        pack_out, ctx->stream);
     CK(cudaGetLastError());
     ctx->st.kernel_launches += 1;
     ctx->st.M = M;
@@ -791,7 +794,7 @@ int esacb200_forward_sharded(esacb200_ctx* ctx, const float* coords, int E, int 
     if (!ctx->nccl_comm) return fail(ctx, ESACB200_ERR_ARG, "no communicator: call esacb200_comm_init first");
     if (!out_pose || (M > 0 && (!coords || !assign))) return fail(ctx, ESACB200_ERR_ARG, "null pointer argument");
     const int world = ctx->comm_world;
-    const size_t rec = (size_t)M_pad + 19;
+    const size_t rec = (size_t)M_pad + kPackTail;
     CK(ctx->gathered.ensure((world + 1) * rec * 8));
     double* mine = ctx->gathered.as<double>() + (size_t)world * rec;
     int rc = enqueue_forward_record(ctx, coords, E, H, W, assign, assign_stride, M, M_pad, shiftX, shiftY, f, ppx, ppy, tau, alpha,
@@ -970,7 +973,8 @@ int esacb200_refine_poses(esacb200_ctx* ctx, const float* coords, int E, int H, 
 static int backward_impl(esacb200_ctx* ctx, const float* coords, float* grads, int E, int H, int W, const int64_t* assign,
                          int64_t assign_stride, int M, const float* gt_pose, float wRot, float wTrans, float cut, int shiftX,
                          int shiftY, float f, float ppx, float ppy, float tau, float alpha, float beta, float maxReproj, int sub,
-                         esacb200_exchange_fn exchange, void* user, double* out_loss, bool use_nccl = false) {
+                         esacb200_exchange_fn exchange, void* user, double* out_loss, bool use_nccl = false,
+                         bool reduce_grads = false) {
     if (!ctx) return ESACB200_ERR_ARG;
     DeviceGuard device_guard(ctx->device);
     if (!coords || !assign || !grads || !gt_pose) return fail(ctx, ESACB200_ERR_ARG, "null pointer argument");
@@ -988,6 +992,14 @@ static int backward_impl(esacb200_ctx* ctx, const float* coords, float* grads, i
         CK(ctx->grads.ensure(cbytes));
         CK(cudaMemcpyAsync(ctx->grads.p, grads, cbytes, cudaMemcpyHostToDevice, ctx->stream));
         d_grads = ctx->grads.as<float>();
+    }
+    // hypothesis-major sharding: every rank holds all planes and a slice of the hypotheses, so the gradient slices overlap:
+    // the local gradient goes to a zeroed work buffer, is summed over the ranks and only then added to the caller's tensor
+    float* d_dst = d_grads;
+    if (reduce_grads) {
+        CK(ctx->grads_work.ensure(cbytes));
+        CK(cudaMemsetAsync(ctx->grads_work.p, 0, cbytes, ctx->stream));
+        d_grads = ctx->grads_work.as<float>();
     }
     rc = stage_inputs(ctx, pl, coords, assign, assign_stride);
     if (rc) return rc;
@@ -1087,6 +1099,13 @@ static int backward_impl(esacb200_ctx* ctx, const float* coords, float* grads, i
     launch_backward(b, M, ctx->stream);
     CK(cudaGetLastError());
     ctx->st.kernel_launches += 5;
+    if (reduce_grads) {
+        CKN(nccl_api().AllReduce(d_grads, d_grads, (size_t)P.E * 3 * P.N, kNcclFloat32, kNcclSum, ctx->nccl_comm, ctx->stream));
+        launch_add_inplace(d_dst, d_grads, (size_t)P.E * 3 * P.N, ctx->stream);
+        CK(cudaGetLastError());
+        ctx->st.kernel_launches += 2;
+        d_grads = d_dst;
+    }
     mark(ctx, EV_BWD);
     if (grads_on_host) CK(cudaMemcpyAsync(grads, d_grads, cbytes, cudaMemcpyDeviceToHost, ctx->stream));
     CK(cudaMemcpyAsync(ctx->h_out + 20, sc, 8 * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
@@ -1133,13 +1152,13 @@ int esacb200_backward_sharded(esacb200_ctx* ctx, const float* coords, float* gra
 int esacb200_backward_sharded_nccl(esacb200_ctx* ctx, const float* coords, float* grads, int E, int H, int W,
                                    const int64_t* assign, int64_t assign_stride, int M, const float* gt_pose, float wRot,
                                    float wTrans, float cut, int shiftX, int shiftY, float f, float ppx, float ppy, float tau,
-                                   float alpha, float beta, float maxReproj, int sub, double* out_loss) try {
+                                   float alpha, float beta, float maxReproj, int sub, int reduce_grads, double* out_loss) try {
     if (!ctx) return ESACB200_ERR_ARG;
     DeviceGuard device_guard(ctx->device);
     if (!ctx->nccl_comm) return fail(ctx, ESACB200_ERR_ARG, "no communicator: call esacb200_comm_init first");
     if (M > 0)
         return backward_impl(ctx, coords, grads, E, H, W, assign, assign_stride, M, gt_pose, wRot, wTrans, cut, shiftX, shiftY, f, ppx,
-                             ppy, tau, alpha, beta, maxReproj, sub, nullptr, nullptr, out_loss, /*use_nccl=*/true);
+                             ppy, tau, alpha, beta, maxReproj, sub, nullptr, nullptr, out_loss, /*use_nccl=*/true, reduce_grads != 0);
     // no hypotheses here: neutral contributions to both collectives
     begin_call(ctx);
     CK(ctx->stats.ensure(8 * 8));
@@ -1149,6 +1168,22 @@ int esacb200_backward_sharded_nccl(esacb200_ctx* ctx, const float* coords, float
     CKN(nccl_api().AllGather(ctx->stats.as<double>() + 5, ctx->gathered.p, 2, kNcclFloat64, ctx->nccl_comm, ctx->stream));
     CKN(nccl_api().AllReduce(ctx->stats.as<double>() + 4, ctx->stats.as<double>() + 7, 1, kNcclFloat64, kNcclSum, ctx->nccl_comm,
                              ctx->stream));
+    if (reduce_grads) {  // zero contribution to the gradient sum, then the sum is added to this rank's tensor like everywhere
+        if (!grads || E <= 0 || H <= 0 || W <= 0) return fail(ctx, ESACB200_ERR_ARG, "reduce_grads needs the gradient tensor and its shape on every rank");
+        const size_t n = (size_t)E * 3 * H * W;
+        CK(ctx->grads_work.ensure(n * 4));
+        CK(cudaMemsetAsync(ctx->grads_work.p, 0, n * 4, ctx->stream));
+        CKN(nccl_api().AllReduce(ctx->grads_work.p, ctx->grads_work.p, n, kNcclFloat32, kNcclSum, ctx->nccl_comm, ctx->stream));
+        if (is_device_ptr(grads)) {
+            launch_add_inplace(grads, ctx->grads_work.as<float>(), n, ctx->stream);
+        } else {
+            CK(ctx->grads.ensure(n * 4));
+            CK(cudaMemcpyAsync(ctx->grads.p, grads, n * 4, cudaMemcpyHostToDevice, ctx->stream));
+            launch_add_inplace(ctx->grads.as<float>(), ctx->grads_work.as<float>(), n, ctx->stream);
+            CK(cudaMemcpyAsync(grads, ctx->grads.p, n * 4, cudaMemcpyDeviceToHost, ctx->stream));
+        }
+        CK(cudaGetLastError());
+    }
     CK(cudaMemcpyAsync(ctx->h_dbl + 4, ctx->stats.as<double>() + 7, sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
     mark(ctx, EV_END);
     CK(cudaStreamSynchronize(ctx->stream));
@@ -1205,6 +1240,7 @@ int esacb200_backward_batch(esacb200_ctx* ctx, int B, const float* coords, float
         w->refine_jobs_per_group = ctx->refine_jobs_per_group;
         w->sample_prefilter = ctx->sample_prefilter;
         w->hyp_offset = ctx->hyp_offset;
+        w->hyp_stride = ctx->hyp_stride;
         w->score_ppt_opt = ctx->score_ppt_opt;
         w->score_hc_opt = ctx->score_hc_opt;
         w->fixed_seed = 1;

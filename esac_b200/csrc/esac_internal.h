@@ -112,7 +112,7 @@ struct SampleState {
 // Returns the number of kernel launches it enqueued.
 int launch_sample(const float* coords, float4* coords4, const int* assign32, const Problem& P, uint64_t seed, int max_tries,
                   const int* injected, int inj_T, const SampleState* st, int n_lanes, int sm_count, int use_prefilter,
-                  int hyp_offset, Pose* poses, int* cells, int* tries, cudaStream_t stream, cudaStream_t aux,
+                  int hyp_offset, int hyp_stride, Pose* poses, int* cells, int* tries, cudaStream_t stream, cudaStream_t aux,
                   cudaEvent_t ev_fork, cudaEvent_t ev_join, int split_e, const int* perm, const int* offsets,
                   const cudaEvent_t* ev_half);
 
@@ -150,7 +150,9 @@ size_t refine_flag_words(int n_groups, int group);
 void launch_finish_forward(const Pose* poses, const int* winner, const int* assign32, const int* flags, float* out20,
                            cudaStream_t st);
 
-void launch_pack_forward(const double* scores, const float* out20, int M, int M_pad, int expert_offset, double* pack, cudaStream_t st);
+void launch_pack_forward(const double* scores, const float* out20, int M, int M_pad, int expert_offset, int hyp_offset, int hyp_stride,
+                         double* pack, cudaStream_t st);
+constexpr int kPackTail = 21;  // doubles behind the M_pad scores of a shard's record
 void launch_select_gathered(const double* gathered, int world, int M_pad, float* out20, cudaStream_t st);
 
 // --- gating.cu ----------------------------------------------------------------------------
@@ -196,6 +198,7 @@ struct BwdArgs {
 void launch_backward(const BwdArgs& a, int max_jobs, cudaStream_t st);
 // phase split for the multi-GPU path: losses + local expectation only / everything after the loss exchange
 void launch_backward_losses(const BwdArgs& a, cudaStream_t st);
+void launch_add_inplace(float* dst, const float* src, size_t n, cudaStream_t st);
 size_t bwd_hypgrad_bytes();
 int bwd_red_vals();
 int bwd_tiles(int N);

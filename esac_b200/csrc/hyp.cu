@@ -41,7 +41,8 @@ struct SampleArgs {
     const int* injected;  // [M][inj_T][4][2] or null
     int inj_T;
     int use_prefilter;    // 0: every try goes to the exact path (self-check of the prefilter)
-    int hyp_offset;       // global index of local hypothesis 0 (multi-GPU shards draw the stream of the unsharded problem)
+    int hyp_offset;       // global index of local hypothesis h = hyp_offset + h * hyp_stride (multi-GPU shards draw the stream of
+    int hyp_stride;       // the unsharded problem; stride > 1: hypotheses dealt round-robin to the ranks)
     int h_first, h_step, Mg;  // this lane's hypotheses: h_first + k * h_step, k < Mg ...
     const int* perm;          // ... or, when set, the hypotheses of experts [e_lo, e_hi): perm[offsets[e_lo] + k]
     const int* offsets;
@@ -63,7 +64,7 @@ __device__ __forceinline__ void load_try(const SampleArgs& a, int h, int t, int 
         const int* c = a.injected + ((size_t)h * a.inj_T + t) * 8;
         for (int j = 0; j < 4; ++j) { cx[j] = c[2 * j]; cy[j] = c[2 * j + 1]; }
     } else {
-        draw_minimal_set(a.seed, (uint32_t)(h + a.hyp_offset), (uint32_t)t, P.W, P.H, cx, cy);
+        draw_minimal_set(a.seed, (uint32_t)(h * a.hyp_stride + a.hyp_offset), (uint32_t)t, P.W, P.H, cx, cy);
     }
     const float4* pl = a.coords4 + (size_t)a.assign32[h] * P.N;
     for (int j = 0; j < 4; ++j) {
@@ -284,7 +285,7 @@ __global__ void __launch_bounds__(64) emit_kernel(const __grid_constant__ Sample
 // ev_half[0]; lane 1 = the rest, released by ev_half[1], so lane 0 samples while the second half is on the wire.
 int launch_sample(const float* coords, float4* coords4, const int* assign32, const Problem& P, uint64_t seed, int max_tries,
                   const int* injected, int inj_T, const SampleState* st, int n_lanes, int sm_count, int use_prefilter,
-                  int hyp_offset, Pose* poses, int* cells, int* tries, cudaStream_t stream, cudaStream_t aux,
+                  int hyp_offset, int hyp_stride, Pose* poses, int* cells, int* tries, cudaStream_t stream, cudaStream_t aux,
                   cudaEvent_t ev_fork, cudaEvent_t ev_join, int split_e, const int* perm, const int* offsets,
                   const cudaEvent_t* ev_half) {
     int launches = 0;
@@ -298,7 +299,7 @@ int launch_sample(const float* coords, float4* coords4, const int* assign32, con
         SampleArgs a;
         a.coords4 = coords4; a.assign32 = assign32; a.P = P; a.seed = seed;
         a.limit = injected ? (max_tries < inj_T ? max_tries : inj_T) : max_tries;
-        a.injected = injected; a.inj_T = inj_T; a.st = st[g]; a.use_prefilter = use_prefilter; a.hyp_offset = hyp_offset;
+        a.injected = injected; a.inj_T = inj_T; a.st = st[g]; a.use_prefilter = use_prefilter; a.hyp_offset = hyp_offset; a.hyp_stride = hyp_stride > 0 ? hyp_stride : 1;
         a.h_first = g; a.h_step = n_lanes; a.Mg = (P.M - g + n_lanes - 1) / n_lanes;
         a.perm = nullptr; a.offsets = nullptr; a.e_lo = a.e_hi = 0;
         int bound = a.Mg;  // host-side bound on the lane size (grid sizing)

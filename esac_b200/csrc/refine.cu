@@ -696,61 +696,71 @@ __global__ void finish_forward_kernel(const Pose* poses, const int* winner, cons
 
 // Record one shard contributes to the all-gather of the sharded forward, as doubles:
 //   [scores (M_pad; entries >= M are -inf: shards may hold different numbers of hypotheses) | camera pose of the local
-//    winner (16) | global expert id, or -1 on a bad assignment | local winner | M]
-// M == 0 (a shard without hypotheses) gives an all -inf record.
-__global__ void pack_forward_kernel(const double* scores, const float* out20, int M, int M_pad, int expert_offset, double* pack) {
+//    winner (16) | global expert id, or -1 on a bad assignment | local winner | M | hyp_offset | hyp_stride]
+// (local hypothesis k is hypothesis hyp_offset + k * hyp_stride of the unsharded problem).  M == 0 gives an all -inf record.
+__global__ void pack_forward_kernel(const double* scores, const float* out20, int M, int M_pad, int expert_offset, int hyp_offset,
+                                    int hyp_stride, double* pack) {
     const double ninf = __longlong_as_double(0xfff0000000000000ull);  // -inf
-    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < M_pad + 19; i += gridDim.x * blockDim.x) {
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < M_pad + kPackTail; i += gridDim.x * blockDim.x) {
         double v;
         if (i < M_pad) v = i < M ? scores[i] : ninf;
-        else if (M == 0) v = i == M_pad + 18 ? 0. : -1.;
+        else if (i == M_pad + 18) v = (double)M;
+        else if (i == M_pad + 19) v = (double)hyp_offset;
+        else if (i == M_pad + 20) v = (double)hyp_stride;
+        else if (M == 0) v = -1.;
         else if (i < M_pad + 16) v = (double)out20[i - M_pad];
         else if (i == M_pad + 16) v = out20[17] != 0.f ? -1. : (double)out20[16] + (double)expert_offset;
-        else if (i == M_pad + 17) v = (double)out20[18];
-        else v = (double)M;
+        else v = (double)out20[18];
         pack[i] = v;
     }
 }
 
-void launch_pack_forward(const double* scores, const float* out20, int M, int M_pad, int expert_offset, double* pack, cudaStream_t st) {
-    pack_forward_kernel<<<(M_pad + 19 + 255) / 256, 256, 0, st>>>(scores, out20, M, M_pad, expert_offset, pack);
+void launch_pack_forward(const double* scores, const float* out20, int M, int M_pad, int expert_offset, int hyp_offset, int hyp_stride,
+                         double* pack, cudaStream_t st) {
+    pack_forward_kernel<<<(M_pad + kPackTail + 255) / 256, 256, 0, st>>>(scores, out20, M, M_pad, expert_offset, hyp_offset, hyp_stride, pack);
 }
 
 // softMax + draw(training = false) over the gathered records of all shards (esac_util.h:461-530): the first strict maximum in
-// rank-major order (= hypothesis order of the unsharded problem when experts are dealt expert-major).  One block.
+// the hypothesis order of the UNSHARDED problem (global index = the record's hyp_offset + k * hyp_stride).  One block.
 // out20: [0..15] camera pose of the global winner, [16] its expert, [17] 1 if any shard flagged a bad assignment,
-// [18] global index rank * M_pad + local index, [19] owning rank.
+// [18] global hypothesis index, [19] owning rank.
 __global__ void __launch_bounds__(256) select_gathered_kernel(const double* __restrict__ g, int world, int M_pad, float* out20) {
     __shared__ double sbest[8];
-    __shared__ int sidx[8];
+    __shared__ long long sidx[8];
+    __shared__ int srank[8];
     __shared__ int sbad;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int rec = M_pad + 19;
+    const int rec = M_pad + kPackTail;
     if (tid == 0) sbad = 0;
     __syncthreads();
     double best = __longlong_as_double(0xfff0000000000000ull);  // -inf
-    int bi = 0x7fffffff;
+    long long bi = 0x7fffffffffffffffll;
+    int br = 0;
     for (int i = tid; i < world * M_pad; i += blockDim.x) {
         const int r = i / M_pad, k = i - r * M_pad;
-        const double v = g[(size_t)r * rec + k];
-        if (v > best) { best = v; bi = i; }  // ascending i per thread: keeps the first
+        const double* rr = g + (size_t)r * rec;
+        if (k >= (int)rr[M_pad + 18]) continue;
+        const double v = rr[k];
+        const long long gi = (long long)rr[M_pad + 19] + (long long)k * (long long)rr[M_pad + 20];
+        if (v > best || (v == best && gi < bi)) { best = v; bi = gi; br = r; }
     }
     for (int r = tid; r < world; r += blockDim.x)
         if (g[(size_t)r * rec + M_pad + 18] > 0. && g[(size_t)r * rec + M_pad + 16] < 0.) atomicExch(&sbad, 1);
     for (int o = 16; o; o >>= 1) {
         const double ob = __shfl_xor_sync(0xffffffffu, best, o);
-        const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
-        if (ob > best || (ob == best && oi < bi)) { best = ob; bi = oi; }
+        const long long oi = __shfl_xor_sync(0xffffffffu, bi, o);
+        const int orr = __shfl_xor_sync(0xffffffffu, br, o);
+        if (ob > best || (ob == best && oi < bi)) { best = ob; bi = oi; br = orr; }
     }
-    if (lane == 0) { sbest[warp] = best; sidx[warp] = bi; }
+    if (lane == 0) { sbest[warp] = best; sidx[warp] = bi; srank[warp] = br; }
     __syncthreads();
     if (tid == 0) {
         double b = sbest[0];
-        int i = sidx[0];
+        long long i = sidx[0];
+        int r = srank[0];
         for (int w = 1; w < 8; ++w)
-            if (sbest[w] > b || (sbest[w] == b && sidx[w] < i)) { b = sbest[w]; i = sidx[w]; }
-        if (i == 0x7fffffff) i = 0;
-        const int r = i / M_pad;
+            if (sbest[w] > b || (sbest[w] == b && sidx[w] < i)) { b = sbest[w]; i = sidx[w]; r = srank[w]; }
+        if (i == 0x7fffffffffffffffll) { i = 0; r = 0; }
         const double* rr = g + (size_t)r * rec + M_pad;
         for (int k = 0; k < 16; ++k) out20[k] = (float)rr[k];
         out20[16] = (float)rr[16];

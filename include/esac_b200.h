@@ -97,8 +97,11 @@ int esacb200_backward_sharded(esacb200_ctx* ctx, const float* coords, float* gra
  *   pack_out[M_pad..+16)    camera pose of the local winner,
  *   pack_out[M_pad+16]      expert_offset + its expert (or -1 if hypAssignment held an index outside [0,E)),
  *   pack_out[M_pad+17]      its local hypothesis index,        pack_out[M_pad+18]  M,
+ *   pack_out[M_pad+19/20]   options "hyp_offset" / "hyp_stride": local hypothesis k is hypothesis offset + k * stride of the
+ *                           unsharded problem (its minimal-set stream and its place in draw()'s first-maximum order),
  * as doubles into DEVICE memory, stream-ordered on the context's stream.  coords / assign must be device pointers (a host
- * buffer would force the synchronisation this entry exists to avoid).  M may be 0 (coords / assign are then ignored). */
+ * buffer would force the synchronisation this entry exists to avoid).  M may be 0 (coords / assign are then ignored).
+ * The record has M_pad + 21 doubles. */
 int esacb200_forward_pack(esacb200_ctx* ctx, const float* coords, int E, int H, int W, const int64_t* assign,
                           int64_t assign_stride, int M, int M_pad, int shiftX, int shiftY, float focalLength, float ppointX,
                           float ppointY, float inlierThreshold, float inlierAlpha, float inlierBeta, float maxReproj,
@@ -123,12 +126,16 @@ int esacb200_forward_sharded(esacb200_ctx* ctx, const float* coords, int E, int 
                              float maxReproj, int subSampling, int expert_offset, int* out_expert);
 /* esac_backward over all shards (gradient slices are disjoint when experts are dealt expert-major: no gradient collective):
  * all-gather of (max score, sum exp) -> global probabilities; all-reduce of the partial expectations -> *out_loss = the
- * global expected loss on every rank.  Option "hyp_offset" as for esacb200_backward_sharded.  M may be 0. */
+ * global expected loss on every rank.  Option "hyp_offset" as for esacb200_backward_sharded.  M may be 0.
+ * reduce_grads != 0: HYPOTHESIS-major sharding -- every rank holds all E planes and a slice of the hypotheses (the refinement
+ * of the contributing hypotheses then shards too, which expert-major dealing cannot do when the gating concentrates them on
+ * one expert); gradient slices overlap, so the local gradients are summed over the ranks with one ncclAllReduce of E*3*H*W
+ * floats and the sum is added to `grads` on every rank (grads stays "+=", esac.cpp:501-506). */
 int esacb200_backward_sharded_nccl(esacb200_ctx* ctx, const float* coords, float* grads, int E, int H, int W,
                                    const int64_t* assign, int64_t assign_stride, int M, const float* gt_pose, float wLossRot,
                                    float wLossTrans, float lossCut, int shiftX, int shiftY, float focalLength, float ppointX,
                                    float ppointY, float inlierThreshold, float inlierAlpha, float inlierBeta, float maxReproj,
-                                   int subSampling, double* out_loss);
+                                   int subSampling, int reduce_grads, double* out_loss);
 
 /* esac_forward over B images of one shape (the reference's callers loop with batch_size=1, test_esac.py:137):
  * coords float32 [B,E,3,H,W], assign int64 [B,M] (rows contiguous, element stride assign_stride; 0 = one expert for all),

@@ -88,6 +88,32 @@ def _worker(rank, world, port, q):
     ctx.set_seed(5)
     g_e = torch.zeros_like(c_e)
     res["loss_e"] = sharded.backward_sharded(c_e, g_e, a_e, torch.from_numpy(sc.gt_pose), 1.0, 100.0, 100.0, sc.params, hyp_offset=0)
+    # ---- hypothesis-major: every rank holds ALL planes and a contiguous slice of the hypotheses; gradients all-reduced ----
+    Mh = E * Mper
+    cut = (Mh * 3) // 5                      # 72 / 48: the slices cut through an expert
+    lo, hi = (0, cut) if rank == 0 else (cut, Mh)
+    c_all = torch.from_numpy(sc.coords).to(dev)
+    a_h = torch.from_numpy(sc.assign[lo:hi]).to(dev)
+    ctx.set_seed(5)
+    out5 = torch.zeros(4, 4, device=dev)
+    res["expert_hm"] = sharded.forward_sharded(c_all, a_h, out5, sc.params, expert_offset=0, hyp_offset=lo, M_pad=max(cut, Mh - cut))
+    res["pose_hm"] = out5.cpu().numpy()
+    ctx.set_seed(5)
+    g_hm = torch.full_like(c_all, 0.5)       # += semantics survive the reduction
+    res["loss_hm"] = sharded.backward_sharded(c_all, g_hm, a_h, torch.from_numpy(sc.gt_pose), 1.0, 100.0, 100.0, sc.params,
+                                              hyp_offset=lo, reduce_grads=True)
+    res["grads_hm"] = g_hm.cpu().numpy() - 0.5
+    # ---- the same dealt round-robin (hypothesis h -> rank h % 2): hyp_offset = rank, hyp_stride = 2 ----
+    a_s = torch.from_numpy(np.ascontiguousarray(sc.assign[rank::2])).to(dev)
+    ctx.set_seed(5)
+    out6 = torch.zeros(4, 4, device=dev)
+    res["expert_hs"] = sharded.forward_sharded(c_all, a_s, out6, sc.params, expert_offset=0, hyp_offset=rank, hyp_stride=2, M_pad=(Mh + 1) // 2)
+    res["pose_hs"] = out6.cpu().numpy()
+    ctx.set_seed(5)
+    g_hs = torch.zeros_like(c_all)
+    res["loss_hs"] = sharded.backward_sharded(c_all, g_hs, a_s, torch.from_numpy(sc.gt_pose), 1.0, 100.0, 100.0, sc.params,
+                                              hyp_offset=rank, hyp_stride=2, reduce_grads=True)
+    res["grads_hs"] = g_hs.cpu().numpy()
     sharded.destroy_comm(rank)
     if rank == 0:  # the unsharded problem on one GPU
         ctx.set_seed(5)
@@ -122,13 +148,16 @@ def test_two_gpu_sharding_reproduces_single_gpu():
     scale = max(np.abs(ref["ref_grads"]).max(), 1e-12)
     for r in (0, 1):
         sl = slice(ref["starts"][r], ref["starts"][r] + ref["sizes"][r])
-        for tag in ("_t", "", "_h", "_e"):          # torch transport, library NCCL, host tensors, empty shard on rank 1
+        for tag in ("_t", "", "_h", "_e", "_hm", "_hs"):   # torch transport, library NCCL, host tensors, empty shard, hypothesis-major
             assert res[r]["expert" + tag] == ref["ref_expert"], tag
             assert np.allclose(res[r]["pose" + tag], ref["ref_pose"], atol=1e-6), tag
-        for tag in ("_t", "", "_e"):
+        for tag in ("_t", "", "_e", "_hm", "_hs"):
             assert abs(res[r]["loss" + tag] - ref["ref_loss"]) < 1e-9 * max(1.0, abs(ref["ref_loss"])), tag
         for tag in ("_t", ""):
             assert np.abs(res[r]["grads" + tag] - ref["ref_grads"][sl]).max() / scale < 1e-6, tag
+        # hypothesis-major: the rank-summed gradient of the whole tensor on every rank (float sums in a different order)
+        assert np.abs(res[r]["grads_hm"] - ref["ref_grads"]).max() / scale < 1e-5
+        assert np.abs(res[r]["grads_hs"] - ref["ref_grads"]).max() / scale < 1e-5
     assert np.abs(ref["ref_grads"]).max() > 0
 
 

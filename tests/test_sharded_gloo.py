@@ -13,13 +13,14 @@ from esac_b200 import sharded
 
 def test_select_global_is_first_strict_maximum():
     M = 5
-    g = np.zeros((3, M + 19))
+    g = np.zeros((3, M + 21))
     g[0, :M] = [1, 2, 3, 2, 1]
     g[1, :M] = [3, 9, 9, 0, 0]       # tie inside rank 1: the first one wins
     g[2, :M] = [9, 0, 0, 0, 0]       # tie across ranks: the lower global index wins
     for r in range(3):
         g[r, M:M + 16] = np.eye(4).reshape(-1) * (r + 1)
         g[r, M + 16] = 10 + r
+        g[r, M + 18:M + 21] = [M, r * M, 1]   # M, hyp_offset, hyp_stride
     w, rank, pose, expert, probs = sharded.select_global(g, M)
     assert (w, rank, expert) == (6, 1, 11)
     assert pose[0, 0] == 2.0 and abs(probs.sum() - 1) < 1e-12
@@ -91,11 +92,13 @@ def test_forward_sharded_unequal_and_empty_shards_gloo():
 
 def test_select_global_ignores_padding():
     M_pad = 4
-    g = np.full((2, M_pad + 19), -1.0)
+    g = np.full((2, M_pad + 21), -1.0)
     g[0, :M_pad] = [5.0, -np.inf, -np.inf, -np.inf]      # rank 0 holds one hypothesis
     g[1, :M_pad] = [1.0, 9.0, 9.0, 2.0]
     g[1, M_pad:M_pad + 16] = np.eye(4).reshape(-1) * 3
     g[1, M_pad + 16] = 7
+    g[0, M_pad + 18:M_pad + 21] = [1, 0, 1]
+    g[1, M_pad + 18:M_pad + 21] = [4, 1, 1]
     w, rank, pose, expert, probs = sharded.select_global(g, M_pad)
     assert (w, rank, expert) == (M_pad + 1, 1, 7) and pose[0, 0] == 3.0
     assert probs[1] == 0.0 and abs(probs.sum() - 1) < 1e-12
@@ -131,3 +134,18 @@ def test_backward_exchange_world2_gloo():
         rank, g, tot = q.get(timeout=5)
         assert abs(g[0] - 9.0) < 1e-15 and abs(g[1] - np.exp(allsc - 9.0).sum()) < 1e-12
         assert abs(tot[0] - 0.75) < 1e-15
+
+
+def test_select_global_breaks_ties_in_the_unsharded_order_with_strided_shards():
+    """Hypotheses dealt round-robin (hyp_stride = world): a tie between global hypotheses 3 (rank 1, local 1) and 4 (rank 0,
+    local 2) goes to hypothesis 3 although rank 0 comes first in the gathered buffer."""
+    M_pad = 3
+    g = np.full((2, M_pad + 21), -1.0)
+    g[0, :M_pad] = [1.0, 2.0, 8.0]     # global 0, 2, 4
+    g[1, :M_pad] = [0.0, 8.0, 3.0]     # global 1, 3, 5
+    for r in range(2):
+        g[r, M_pad:M_pad + 16] = np.eye(4).reshape(-1) * (r + 1)
+        g[r, M_pad + 16] = r
+        g[r, M_pad + 18:M_pad + 21] = [3, r, 2]
+    w, rank, pose, expert, _ = sharded.select_global(g, M_pad)
+    assert (w, rank, expert) == (M_pad + 1, 1, 1) and pose[0, 0] == 2.0
