@@ -49,14 +49,16 @@ class Scene:
 
 def make_scene(E=1, H=60, W=80, M=64, sub=8, seed=0, outlier_frac=0.4, noise=0.02, f=525.0,
                outdoor=False, gt_mass=0.6, per_expert=False, shiftX=0, shiftY=0, world_offset=0.0,
-               active_only=True) -> Scene:
+               active_only=True, unit_scale=1.0, alpha=100.0) -> Scene:
     """One synthetic image worth of expert predictions.
 
     per_expert=False: ``assign`` is a multinomial draw of M hypotheses from a gating vector with
     ``gt_mass`` on the ground-truth expert (reference semantics: M hypotheses in total,
     test_esac.py:175).  per_expert=True: M hypotheses for every expert (M*E total, BASELINE.json's
     "256 hyp x E experts" wording).  Experts that receive no hypothesis keep all-zero planes when
-    ``active_only`` (test_esac.py:157,183-185)."""
+    ``active_only`` (test_esac.py:157,183-185).  ``unit_scale`` multiplies every length (maps and ground-truth translation:
+    metres -> e.g. millimetres) and ``alpha`` sets the score scale; the clamp fixtures use both
+    (tests/golden/make_ref_golden.py)."""
     rng = np.random.default_rng(1305 + seed)
     img_w, img_h = W * sub, H * sub
     ppx, ppy = img_w / 2.0, img_h / 2.0
@@ -107,7 +109,11 @@ def make_scene(E=1, H=60, W=80, M=64, sub=8, seed=0, outlier_frac=0.4, noise=0.0
     if active_only:
         hist = np.bincount(assign, minlength=E)
         coords[hist == 0] = 0.0
-    return Scene(coords, assign, gt_pose, gt_e, float(f), float(ppx), float(ppy), int(sub), shiftX, shiftY)
+    if unit_scale != 1.0:
+        coords = (coords * np.float32(unit_scale)).astype(np.float32)
+        gt_pose = gt_pose.copy()
+        gt_pose[:3, 3] *= np.float32(unit_scale)
+    return Scene(coords, assign, gt_pose, gt_e, float(f), float(ppx), float(ppy), int(sub), shiftX, shiftY, alpha=float(alpha))
 
 
 def pose_error(T_est: np.ndarray, T_gt: np.ndarray) -> tuple[float, float]:

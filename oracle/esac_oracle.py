@@ -553,7 +553,8 @@ def d_pnp(img, obj, K, eps=np.float32(0.001)):
     return jac
 
 
-def d_sm_score(coords, assign, sampling, hyps, losses, probs, repro_errs, jacobeans, K, alpha, beta, tau, max_reproj):
+def d_sm_score(coords, assign, sampling, hyps, losses, probs, repro_errs, jacobeans, K, alpha, beta, tau, max_reproj,
+               clamp_thresh=10.0, clamp_log=None):
     """esac_derivative.h:347-420 (dSMScore) + 205-324 (dScore).  Returns list of [N_rowmajor, 3]
     f64 (index y*W + x) per hypothesis, zeros for hypotheses below PROB_THRESH."""
     H, W = sampling.shape[:2]
@@ -577,8 +578,10 @@ def d_sm_score(coords, assign, sampling, hyps, losses, probs, repro_errs, jacobe
         fac = np.float32(np.float32(np.float32(alpha) / np.float32(W)) / np.float32(H))
         dRe = dRe * float(fac)
         dHdO = d_pnp(hyps[h].img, hyps[h].obj, K)
-        if get_max(dHdO) > 10:
+        if get_max(dHdO) > clamp_thresh:  # esac_derivative.h:287, "clamping for stability"
             dHdO = np.zeros_like(dHdO)
+            if clamp_log is not None:
+                clamp_log.append(h)
         rot, _ = cv2.Rodrigues(hyps[h].rvec)
         pts3, pts2 = _collect(coords, e, sampling)  # p = x*H + y
         w = dRe.T.reshape(-1)  # same ordering
@@ -644,11 +647,16 @@ class BackwardTrace:
     losses: list
     grad_I: list
     grad_II: list
+    clamped_jr: list = None     # hypotheses whose max|J_R| > 10 zeroed path I (esac.cpp:436-437)
+    clamped_dpnp: list = None   # hypotheses whose max|dPNP| > 10 zeroed the minimal-set term (esac_derivative.h:287)
 
 
 def backward(coords, out_grads, assign, gt_pose, w_rot, w_trans, cut, shiftX, shiftY, f, ppx, ppy, tau, alpha,
-             beta, max_reproj, sub, seed=1305, injected_cells=None, max_tries=MAX_SAMPLING_TRIES, trace=False, mt=None):
-    """esac.cpp:213-511.  out_grads f32 [E,3,H,W] is ACCUMULATED in place.  Returns expected loss."""
+             beta, max_reproj, sub, seed=1305, injected_cells=None, max_tries=MAX_SAMPLING_TRIES, trace=False, mt=None,
+             clamp_thresh=10.0):
+    """esac.cpp:213-511.  out_grads f32 [E,3,H,W] is ACCUMULATED in place.  Returns expected loss.
+    ``clamp_thresh`` is the reference's 10 (esac.cpp:436-437, esac_derivative.h:287); tests raise it to infinity to show what
+    the gradient would be without the clamps, i.e. that a fixture really trips them."""
     coords = np.asarray(coords)
     assert coords.dtype == np.float32 and coords.ndim == 4
     assert out_grads.dtype == np.float32 and out_grads.shape == coords.shape
@@ -684,6 +692,7 @@ def backward(coords, out_grads, assign, gt_pose, w_rot, w_trans, cut, shiftX, sh
     # ---- path I (esac.cpp:373-463) -----------------------------------------------------------
     gt_r, gt_t = trans2pose(gtT)
     grad_I = [None] * M
+    clamped_jr, clamped_dpnp = [], []
     for h in range(M):
         if probs[h] < PROB_THRESH:
             continue
@@ -708,8 +717,9 @@ def backward(coords, out_grads, assign, gt_pose, w_rot, w_trans, cut, shiftX, sh
                 jtj = jr.T @ jr
                 inv = cv2.invert(jtj, flags=cv2.DECOMP_SVD)[1]
                 JR = -inv @ jr.T  # 6 x n
-                if get_max(JR) > 10:
+                if get_max(JR) > clamp_thresh:
                     JR = np.zeros_like(JR)
+                    clamped_jr.append(h)
                 rot, _ = cv2.Rodrigues(ref[h][0])
                 dNdO = d_project_d_obj_batch(img, obj, rot, ref[h][1], K, max_reproj)  # n x 3
                 for k in range(len(xs)):
@@ -718,7 +728,8 @@ def backward(coords, out_grads, assign, gt_pose, w_rot, w_trans, cut, shiftX, sh
         dl = d_loss(ref[h][0], ref[h][1], gt_r, gt_t, w_rot, w_trans, cut)
         grad_I[h] = (dl @ dHyp).reshape(N, 3)
     # ---- path II (esac.cpp:472-486) ----------------------------------------------------------
-    grad_II = d_sm_score(coords, assign, sampling, hyps, losses, probs, errs, jacs, K, alpha, beta, tau, max_reproj)
+    grad_II = d_sm_score(coords, assign, sampling, hyps, losses, probs, errs, jacs, K, alpha, beta, tau, max_reproj,
+                         clamp_thresh, clamped_dpnp)
     # ---- assembly (esac.cpp:491-508): float += double, sequential over h ----------------------
     for h in range(M):
         if probs[h] < PROB_THRESH:
@@ -727,5 +738,5 @@ def backward(coords, out_grads, assign, gt_pose, w_rot, w_trans, cut, shiftX, sh
         tot = (probs[h] * grad_I[h] + grad_II[h]).reshape(H, W, 3).transpose(2, 0, 1)
         out_grads[e] = (out_grads[e].astype(np.float64) + tot).astype(np.float32)
     if trace:
-        return float(expected), BackwardTrace(hyps, scores, probs, ref, imaps, losses, grad_I, grad_II)
+        return float(expected), BackwardTrace(hyps, scores, probs, ref, imaps, losses, grad_I, grad_II, clamped_jr, clamped_dpnp)
     return float(expected)

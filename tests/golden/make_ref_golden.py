@@ -31,6 +31,12 @@ SMALL = {
     "ref_ensemble3_30x40_shift": dict(E=3, H=30, W=40, M=48, sub=8, seed=42, shiftX=2, shiftY=-3),
     "ref_portrait_40x27": dict(E=2, H=40, W=27, M=32, sub=8, seed=43),
     "ref_world_scale_24x32": dict(E=2, H=24, W=32, M=32, sub=8, seed=48, outdoor=True, world_offset=700.0),
+    # the two "clamping for stability" sites (esac.cpp:436-437 max|J_R| > 10, esac_derivative.h:287 max|dPNP| > 10):
+    # tiny maps make the minimal sets clustered (dPNP of 9 of 12 hypotheses exceeds 10), lengths in units of 1/7000 m
+    # push J_R = -(J^T J)^-1 J^T over 10 for every contributing hypothesis, 1/5000 m keeps it just below
+    "ref_clamp_dpnp_9x12": dict(E=1, H=9, W=12, M=12, sub=8, seed=71, outlier_frac=0.1, noise=0.01, alpha=5.0),
+    "ref_clamp_jr_on_12x16": dict(E=2, H=12, W=16, M=12, sub=8, seed=63, outlier_frac=0.3, noise=0.002, unit_scale=7000.0),
+    "ref_clamp_jr_off_12x16": dict(E=2, H=12, W=16, M=12, sub=8, seed=63, outlier_frac=0.3, noise=0.002, unit_scale=5000.0),
 }
 LARGE = {
     "ref_mid_4x120x160": dict(E=4, H=120, W=160, M=48, sub=4, seed=45),
@@ -107,7 +113,18 @@ if __name__ == "__main__":
         assert o_e == e and np.abs(o_pose - pose).max() <= 1e-6, (name, o_e, e, np.abs(o_pose - pose).max())
         top = np.sort(np.array(tr.scores))[::-1]
         assert top[0] - top[1] > 1e-2, f"{name}: near-tie at the top ({top[0] - top[1]:.2e}) -- pick another seed"
-        common = dict(scene_kw=np.array(repr(kw)), assign=sc.assign, gt_pose=sc.gt_pose, params=np.array(sc.params, np.float64),
+        # which hypotheses trip the two clamps, and how far the gradient would move without them (oracle view)
+        g_o = np.zeros_like(sc.coords)
+        _, bt = O.backward(sc.coords, g_o, sc.assign, sc.gt_pose, *LOSS_ARGS, *sc.params, mt=O.ThreadRandStream(1305), trace=True)
+        extra = {}
+        if name.startswith("ref_clamp"):
+            g_u = np.zeros_like(sc.coords)
+            O.backward(sc.coords, g_u, sc.assign, sc.gt_pose, *LOSS_ARGS, *sc.params, mt=O.ThreadRandStream(1305),
+                       clamp_thresh=np.inf)
+            extra = dict(clamped_jr=np.array(bt.clamped_jr, np.int32), clamped_dpnp=np.array(bt.clamped_dpnp, np.int32),
+                         unclamped_grad_diff=float(np.abs(g_u - g_o).max()))
+            print(f"  clamps: J_R {bt.clamped_jr}, dPNP {bt.clamped_dpnp}, |g(no clamp) - g| max {extra['unclamped_grad_diff']:.3g}")
+        common = dict(**extra, scene_kw=np.array(repr(kw)), assign=sc.assign, gt_pose=sc.gt_pose, params=np.array(sc.params, np.float64),
                       loss_args=np.array(LOSS_ARGS), cells=cells, tries=tries, expert=e, pose=pose, loss=loss,
                       oracle_scores=np.array(tr.scores), oracle_winner=tr.winner, oracle_rounds=tr.rounds,
                       oracle_inliers=int(tr.inlier_map.sum()) if tr.inlier_map is not None else 0)

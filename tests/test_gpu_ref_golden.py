@@ -4,6 +4,8 @@ tests/golden/make_ref_golden.py -- the unmodified esac.cpp on the real OpenCV, s
 The fixtures carry every minimal set the reference tried; they are injected (esacb200_inject_cells) so the CUDA path judges
 the same candidates in the same order.  Tolerances are BASELINE.json's: 1e-3 deg / 1e-3 cm on the pose; gradients to 1e-3 of
 the largest entry; the expected loss to 1e-6 relative."""
+import ast
+
 import numpy as np
 import pytest
 
@@ -40,7 +42,8 @@ def test_forward_and_backward_match_the_compiled_reference(api, path):
     assert e == int(z["expert"]) and st["winner"] == int(z["oracle_winner"])
     assert st["refine_rounds"] == int(z["oracle_rounds"])
     rot, trans = pose_error(out, z["pose"])
-    assert rot < 1e-3 and trans < 1e-5, (rot, trans)
+    unit = float(ast.literal_eval(str(z["scene_kw"])).get("unit_scale", 1.0))  # map units per metre: 1e-3 cm = 1e-5 m
+    assert rot < 1e-3 and trans < 1e-5 * unit, (rot, trans)
     # ---- esac.backward ----
     api.inject_cells(cells)
     g = np.zeros_like(coords)
@@ -50,6 +53,10 @@ def test_forward_and_backward_match_the_compiled_reference(api, path):
     if "grads" in z.files:
         scale = max(np.abs(z["grads"]).max(), 1e-12)
         assert np.abs(g - z["grads"]).max() / scale < 1e-3
+        if "unclamped_grad_diff" in z.files and len(z["clamped_jr"]) + len(z["clamped_dpnp"]):
+            # clamp fixtures (esac.cpp:436-437, esac_derivative.h:287): without the `> 10` clamps the gradient would sit this
+            # far away (tests/test_oracle.py::test_clamp_fixtures_really_trip_the_clamps), i.e. >= 50 tolerances
+            assert float(z["unclamped_grad_diff"]) / scale > 0.05
     else:
         scale = float(z["grad_max"])
         assert abs(np.abs(g).max() - scale) < 1e-3 * scale

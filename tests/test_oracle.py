@@ -232,6 +232,35 @@ def test_oracle_reproduces_the_compiled_reference_fixtures(path):
     assert [[list(c) for c in h.cells] for h in tr.hyps] == z["cells"][:, -1].tolist()
     g = np.zeros_like(z["coords"])
     w_rot, w_trans, cut = (float(v) for v in z["loss_args"])
-    loss = O.backward(z["coords"], g, z["assign"], z["gt_pose"], w_rot, w_trans, cut, *params, mt=O.ThreadRandStream(1305))
+    loss, bt = O.backward(z["coords"], g, z["assign"], z["gt_pose"], w_rot, w_trans, cut, *params, mt=O.ThreadRandStream(1305),
+                          trace=True)
     assert abs(loss - float(z["loss"])) <= 1e-9 * max(1.0, abs(float(z["loss"])))
     assert np.abs(g - z["grads"]).max() <= 1e-6 * np.abs(z["grads"]).max()
+    if "clamped_jr" in z.files:  # the "clamping for stability" fixtures (esac.cpp:436-437, esac_derivative.h:287)
+        assert bt.clamped_jr == z["clamped_jr"].tolist() and bt.clamped_dpnp == z["clamped_dpnp"].tolist()
+
+
+def test_clamp_fixtures_really_trip_the_clamps():
+    """The reference's gradient on these fixtures is only reproduced WITH the two `> 10` clamps: without them the oracle's
+    gradient moves by far more than the parity tolerance (1e-3 of the largest entry), so an implementation that matches the
+    fixtures provably clamps where the reference does.  The J_R pair brackets the threshold: same scene in units of 1/7000 m
+    (every contributing hypothesis clamped, path I vanishes) and 1/5000 m (none clamped)."""
+    from ref_golden_util import GOLD_DIR, params_of
+    seen = {}
+    for name in ("ref_clamp_dpnp_9x12", "ref_clamp_jr_on_12x16", "ref_clamp_jr_off_12x16"):
+        z = np.load(GOLD_DIR / f"{name}.npz")
+        seen[name] = z
+        g_ref = z["grads"]
+        g_no = np.zeros_like(g_ref)
+        w_rot, w_trans, cut = (float(v) for v in z["loss_args"])
+        O.backward(z["coords"], g_no, z["assign"], z["gt_pose"], w_rot, w_trans, cut, *params_of(z), mt=O.ThreadRandStream(1305),
+                   clamp_thresh=np.inf)
+        moved = np.abs(g_no - g_ref).max() / np.abs(g_ref).max()
+        if name == "ref_clamp_jr_off_12x16":
+            assert len(z["clamped_jr"]) == 0
+        else:
+            assert moved > 0.05, (name, moved)
+    assert len(seen["ref_clamp_dpnp_9x12"]["clamped_dpnp"]) == 9 and len(seen["ref_clamp_dpnp_9x12"]["clamped_jr"]) == 0
+    assert len(seen["ref_clamp_jr_on_12x16"]["clamped_jr"]) == 3
+    # the clamp removes path I altogether: the gradient collapses by four orders of magnitude between the two unit scales
+    assert np.abs(seen["ref_clamp_jr_on_12x16"]["grads"]).max() < 1e-3 * np.abs(seen["ref_clamp_jr_off_12x16"]["grads"]).max()
