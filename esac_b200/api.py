@@ -89,6 +89,10 @@ def load_library() -> C.CDLL:
     lib.esacb200_refine_poses.argtypes = [vp, vp, i32, i32, i32, vp, i64, i32, vp, i32, i32, f32, f32, f32, f32, f32, i32, vp, vp]
     lib.esacb200_get_refine_profile.argtypes = [vp, vp]
     lib.esacb200_get_refine_profile.restype = i32
+    lib.esacb200_get_sample_trace.argtypes = [vp, vp]
+    lib.esacb200_get_sample_trace.restype = i32
+    lib.esacb200_get_sample_profile.argtypes = [vp, vp]
+    lib.esacb200_get_sample_profile.restype = i32
     lib.esacb200_get_stats.argtypes = [vp, C.POINTER(Stats)]
     lib.esacb200_get_hypotheses.argtypes = [vp, vp, vp, vp, vp, vp, vp, vp]
     lib.esacb200_device_info.argtypes = [vp, C.POINTER(i32), C.c_char_p, i32]
@@ -196,6 +200,24 @@ class Context:
         """Phase cycle counters of the last refinement (option "refine_profile" = 1), see include/esac_b200.h."""
         out = np.zeros(16, np.int64)
         self.check(self.lib.esacb200_get_refine_profile(self.handle, out.ctypes.data))
+        return out
+
+    def sample_profile(self) -> dict:
+        out = np.zeros(8, np.int64)
+        self.check(self.lib.esacb200_get_sample_profile(self.handle, out.ctypes.data))
+        d = {"tries_prefiltered": int(out[0]), "survivors_judged": int(out[1]), "waves": int(out[2]),
+             "left_to_tail": int(out[3]), "accepted_staged": int(out[4]), "lanes": int(out[5])}
+        return d
+
+    def sample_trace(self) -> np.ndarray:
+        """[lane, wave, kernel (0 prefilter, 1 exact), (start, end)] in ns relative to the first stamp; -1 where nothing ran."""
+        raw = np.zeros(512, np.uint64)
+        self.check(self.lib.esacb200_get_sample_trace(self.handle, raw.ctypes.data))
+        t = raw.reshape(4, 32, 2, 2)
+        ran = t[..., 0] != np.uint64(0xFFFFFFFFFFFFFFFF)
+        t0 = t[..., 0][ran].min() if ran.any() else np.uint64(0)
+        out = np.full(t.shape, -1, np.int64)
+        out[ran] = (t[ran] - t0).astype(np.int64)
         return out
 
     def copy_last_scores(self, dst):

@@ -59,7 +59,8 @@ struct esacb200_ctx {
     cudaStream_t own_stream = nullptr;
     cudaStream_t copy_stream = nullptr;
     cudaStream_t aux_stream = nullptr;   // second lane of the sampling stage
-    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+    cudaStream_t aux_more[2] = {nullptr, nullptr};  // third and fourth lane (option sample_groups; no gain measured)
+    cudaEvent_t ev_fork = nullptr, ev_join = nullptr, ev_join_more[2] = {nullptr, nullptr};
     int sample_groups = 2;
     int upload_split = 1;
     cudaEvent_t ev_copied[2] = {nullptr, nullptr}, ev_consumed[2] = {nullptr, nullptr};
@@ -73,6 +74,13 @@ struct esacb200_ctx {
     int refine_profile = 0;    // 1: block 0 of the refinement kernel records phase cycle counts (esacb200_get_refine_profile)
     int refine_jobs_per_group = 3;
     int sample_prefilter = 1;
+    int sample_span0 = 128;       // tries per hypothesis in the first wave
+    float sample_window = 1.25f;  // later waves: window / acceptance rate
+    int sample_waves = 7;
+    float sample_tail_boost = 1.f;  // window factor once <= 64 hypotheses are left in a lane (x2 more for <= 8)
+    int sample_trace = 0;         // 1: prefilter / exact kernels stamp first-CTA-start / last-CTA-end times (esacb200_get_sample_trace)
+    int smp_groups_last = 0;      // lanes of the last run_sample (diagnostics read-back)
+    int smp_Mg_last = 0;
     int hyp_offset = 0, hyp_stride = 1;
     int score_ppt_opt = 0, score_hc_opt = 0;
     int refine_coresident = 0;
@@ -80,7 +88,7 @@ struct esacb200_ctx {
     // workspace
     DevBuf coords, grads, assign64, assign32, counts, offsets, perm, slot_of, chunks, scalars, centres, poses, poses_ref,
         cells, tries, posepk, part, scores, probs, stats, contrib, masks, rounds, scratch, barrier, out17, inject,
-        losses, red, hypgrad, job_of, gt, smp_int, smp_surv, coords4, coords_alt, assign64_alt, out_batch, prof;
+        losses, red, hypgrad, job_of, gt, smp_int, smp_surv, smp_trace, coords4, coords_alt, assign64_alt, out_batch, prof;
     float* h_out = nullptr;  // pinned staging: 32 floats
     double* h_dbl = nullptr; // pinned staging: 8 doubles
     int inj_M = 0, inj_T = 0;
@@ -328,14 +336,15 @@ int run_sample(esacb200_ctx* ctx, const Plan& pl, uint64_t seed) {
     const int cap = 1 << 19;       // per group
     const int cap_acc = 1 << 15;
     // two lanes pay once a wave's kernels are long enough to overlap (full-resolution maps, or very many hypotheses)
-    const int G = pl.split_e ? 2 : ((ctx->sample_groups > 1 && ctx->aux_stream && P.M >= 64 && (P.N >= 65536 || P.M >= 1024)) ? 2 : 1);
+    int G = pl.split_e ? 2 : ((ctx->sample_groups > 1 && ctx->aux_stream && P.M >= 64 && (P.N >= 65536 || P.M >= 1024)) ? ctx->sample_groups : 1);
+    if (G > 2 && (!ctx->aux_more[0] || !ctx->aux_more[1] || P.M < 512)) G = 2;
     const int Mg = pl.split_e ? P.M : (P.M + G - 1) / G;  // capacity of a lane's work list
     // ints: [best: 2M] [base: M] [ovf: M] then per group [list: 2*Mg] [counters: 8]
     const size_t per_group_ints = (size_t)2 * Mg + 8;
     CK(ctx->smp_int.ensure(((size_t)P.M * 4 + G * per_group_ints) * 4 + 8));
     const size_t per_group_bytes = (size_t)cap * sizeof(int2) + (size_t)cap_acc * sizeof(Accepted);
     CK(ctx->smp_surv.ensure(G * per_group_bytes));
-    SampleState st[2];
+    SampleState st[4];
     int* b = ctx->smp_int.as<int>() + 2 * (size_t)P.M;
     for (int g = 0; g < G; ++g) {
         st[g].best = ctx->smp_int.as<unsigned long long>();  // 8-byte aligned: first in the buffer
@@ -351,12 +360,24 @@ int run_sample(esacb200_ctx* ctx, const Plan& pl, uint64_t seed) {
         st[g].M = Mg;
     }
     CK(ctx->coords4.ensure((size_t)P.E * P.N * sizeof(float4)));
+    unsigned long long* trace = nullptr;
+    if (ctx->sample_trace) {  // 4 lanes x 32 waves x 2 kernels x (start, end)
+        CK(ctx->smp_trace.ensure(512 * 8));
+        CK(cudaMemsetAsync(ctx->smp_trace.p, 0, 512 * 8, ctx->stream));
+        trace = ctx->smp_trace.as<unsigned long long>();
+        launch_trace_init(trace, 256, ctx->stream);
+    }
+    const cudaStream_t lane_streams[4] = {ctx->stream, ctx->aux_stream, ctx->aux_more[0], ctx->aux_more[1]};
+    const cudaEvent_t lane_joins[4] = {nullptr, ctx->ev_join, ctx->ev_join_more[0], ctx->ev_join_more[1]};
     ctx->st.kernel_launches += launch_sample(pl.d_coords, ctx->coords4.as<float4>(), ctx->assign32.as<int>(), P, seed, ctx->max_tries,
                                              ctx->inj_M ? ctx->inject.as<int>() : nullptr, ctx->inj_T, st, G, ctx->sm_count,
                                              ctx->sample_prefilter, ctx->hyp_offset, ctx->hyp_stride, ctx->poses.as<Pose>(), ctx->cells.as<int>(),
-                                             ctx->tries.as<int>(), ctx->stream, ctx->aux_stream, ctx->ev_fork, ctx->ev_join,
-                                             pl.split_e, ctx->perm.as<int>(), ctx->offsets.as<int>(), ctx->ev_copied);
+                                             ctx->tries.as<int>(), lane_streams, ctx->ev_fork, lane_joins,
+                                             pl.split_e, ctx->perm.as<int>(), ctx->offsets.as<int>(), ctx->ev_copied,
+                                             ctx->sample_span0, ctx->sample_window, ctx->sample_waves, trace, ctx->sample_tail_boost);
     CK(cudaGetLastError());
+    ctx->smp_groups_last = G;
+    ctx->smp_Mg_last = Mg;
     if (pl.split_e) {
         // both halves have landed (the join orders this stream after lane 1, which waited for the second half): plane centres
         int* sc = ctx->scalars.as<int>();
@@ -554,6 +575,10 @@ int esacb200_create(int device, esacb200_ctx** out) {
         if (cudaStreamCreateWithPriority(&ctx->aux_stream, cudaStreamNonBlocking, hi) != cudaSuccess) { ctx->aux_stream = nullptr; cudaGetLastError(); }
         cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming);
         cudaEventCreateWithFlags(&ctx->ev_join, cudaEventDisableTiming);
+        for (int i = 0; i < 2; ++i) {
+            if (cudaStreamCreateWithPriority(&ctx->aux_more[i], cudaStreamNonBlocking, hi) != cudaSuccess) { ctx->aux_more[i] = nullptr; cudaGetLastError(); }
+            cudaEventCreateWithFlags(&ctx->ev_join_more[i], cudaEventDisableTiming);
+        }
     }
     for (int i = 0; i < 2; ++i) {
         cudaEventCreateWithFlags(&ctx->ev_copied[i], cudaEventDisableTiming);
@@ -580,7 +605,7 @@ void esacb200_destroy(esacb200_ctx* ctx) {
                       &ctx->slot_of, &ctx->chunks, &ctx->scalars, &ctx->centres, &ctx->poses, &ctx->poses_ref, &ctx->cells,
                       &ctx->tries, &ctx->posepk, &ctx->part, &ctx->scores, &ctx->probs, &ctx->stats, &ctx->contrib,
                       &ctx->masks, &ctx->rounds, &ctx->scratch, &ctx->barrier, &ctx->out17, &ctx->inject, &ctx->losses,
-                      &ctx->red, &ctx->hypgrad, &ctx->job_of, &ctx->gt, &ctx->smp_int, &ctx->smp_surv, &ctx->coords4, &ctx->coords_alt, &ctx->assign64_alt, &ctx->out_batch, &ctx->prof, &ctx->gathered, &ctx->grads_work};
+                      &ctx->red, &ctx->hypgrad, &ctx->job_of, &ctx->gt, &ctx->smp_int, &ctx->smp_surv, &ctx->smp_trace, &ctx->coords4, &ctx->coords_alt, &ctx->assign64_alt, &ctx->out_batch, &ctx->prof, &ctx->gathered, &ctx->grads_work};
     for (DevBuf* b : bufs) b->release();
     for (int i = 0; i < EV_COUNT; ++i)
         if (ctx->ev[i]) cudaEventDestroy(ctx->ev[i]);
@@ -594,6 +619,10 @@ void esacb200_destroy(esacb200_ctx* ctx) {
     if (ctx->aux_stream) cudaStreamDestroy(ctx->aux_stream);
     if (ctx->ev_fork) cudaEventDestroy(ctx->ev_fork);
     if (ctx->ev_join) cudaEventDestroy(ctx->ev_join);
+    for (int i = 0; i < 2; ++i) {
+        if (ctx->aux_more[i]) cudaStreamDestroy(ctx->aux_more[i]);
+        if (ctx->ev_join_more[i]) cudaEventDestroy(ctx->ev_join_more[i]);
+    }
     if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
     delete ctx;
 }
@@ -622,8 +651,13 @@ int esacb200_set_option(esacb200_ctx* ctx, const char* key, double v) {
     else if (!strcmp(key, "refine_profile")) ctx->refine_profile = v != 0;
     else if (!strcmp(key, "refine_jobs_per_group")) ctx->refine_jobs_per_group = v < 1 ? 1 : (int)v;
     else if (!strcmp(key, "sample_prefilter")) ctx->sample_prefilter = v != 0;
+    else if (!strcmp(key, "sample_tail_boost")) ctx->sample_tail_boost = v < 1 ? 1.f : (float)v;
+    else if (!strcmp(key, "sample_trace")) ctx->sample_trace = v != 0;
+    else if (!strcmp(key, "sample_span0")) ctx->sample_span0 = v < 128 ? 128 : ((int)v + 127) / 128 * 128;
+    else if (!strcmp(key, "sample_window")) ctx->sample_window = v < 0.05 ? 0.05f : (float)v;
+    else if (!strcmp(key, "sample_waves")) ctx->sample_waves = v < 0 ? 0 : (v > 64 ? 64 : (int)v);
     else if (!strcmp(key, "upload_split")) ctx->upload_split = v != 0;  // host maps in two halves, sampling under the second copy
-    else if (!strcmp(key, "sample_groups")) ctx->sample_groups = v >= 2 ? 2 : 1;  // 2: two interleaved lanes on two streams
+    else if (!strcmp(key, "sample_groups")) ctx->sample_groups = v >= 4 ? 4 : (v >= 2 ? (int)v : 1);  // interleaved lanes, one stream each
     else if (!strcmp(key, "hyp_offset")) ctx->hyp_offset = (int)v;  // global index of local hypothesis 0 (sharded runs)
     else if (!strcmp(key, "hyp_stride")) ctx->hyp_stride = v < 1 ? 1 : (int)v;  // ... of local hypothesis h: offset + h * stride
     else if (!strcmp(key, "score_ppt")) ctx->score_ppt_opt = (int)v;   // 0 = automatic, else 2 / 4 / 8 cells per thread
@@ -1239,6 +1273,7 @@ int esacb200_backward_batch(esacb200_ctx* ctx, int B, const float* coords, float
         w->refine_group_opt = ctx->refine_group_opt;
         w->refine_jobs_per_group = ctx->refine_jobs_per_group;
         w->sample_prefilter = ctx->sample_prefilter;
+        w->sample_tail_boost = ctx->sample_tail_boost;
         w->hyp_offset = ctx->hyp_offset;
         w->hyp_stride = ctx->hyp_stride;
         w->score_ppt_opt = ctx->score_ppt_opt;
@@ -1415,6 +1450,37 @@ int esacb200_get_stats(esacb200_ctx* ctx, esacb200_stats* out) {
     *out = ctx->st;
     return ESACB200_OK;
 }
+
+int esacb200_get_sample_trace(esacb200_ctx* ctx, unsigned long long* out512) try {
+    if (!ctx || !out512) return ESACB200_ERR_ARG;
+    DeviceGuard device_guard(ctx->device);
+    if (!ctx->smp_trace.p) return fail(ctx, ESACB200_ERR_ARG, "no sampling ran with option sample_trace = 1");
+    CK(cudaStreamSynchronize(ctx->stream));
+    CK(cudaMemcpy(out512, ctx->smp_trace.p, 512 * 8, cudaMemcpyDeviceToHost));
+    return ESACB200_OK;
+} ESAC_ABI_CATCH(ctx)
+
+int esacb200_get_sample_profile(esacb200_ctx* ctx, long long* out8) try {
+    if (!ctx || !out8) return ESACB200_ERR_ARG;
+    DeviceGuard device_guard(ctx->device);
+    for (int i = 0; i < 8; ++i) out8[i] = 0;
+    const int G = ctx->smp_groups_last, M = ctx->last_M, Mg = ctx->smp_Mg_last;
+    if (G <= 0 || M <= 0) return fail(ctx, ESACB200_ERR_ARG, "no previous call");
+    CK(cudaStreamSynchronize(ctx->stream));
+    const size_t per_group_ints = (size_t)2 * Mg + 8;
+    for (int g = 0; g < G; ++g) {
+        int c[8];
+        const int* src = ctx->smp_int.as<int>() + 4 * (size_t)M + g * per_group_ints + 2 * (size_t)Mg;
+        CK(cudaMemcpy(c, src, sizeof(c), cudaMemcpyDeviceToHost));
+        out8[0] += (unsigned)c[5];
+        out8[1] += (unsigned)c[6];
+        out8[2] = out8[2] > c[7] ? out8[2] : c[7];
+        out8[3] += c[0];
+        out8[4] += c[2];
+    }
+    out8[5] = G;
+    return ESACB200_OK;
+} ESAC_ABI_CATCH(ctx)
 
 int esacb200_get_hypotheses(esacb200_ctx* ctx, double* poses6, int32_t* cells, int32_t* tries, double* scores,
                             double* probs, double* refined6, double* losses) try {

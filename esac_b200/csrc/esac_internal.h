@@ -106,15 +106,18 @@ struct SampleState {
     int* list;      // [2M] unresolved hypotheses (second half: scratch for rebuilding)
     int2* surv;     // [cap] (hypothesis, try) pairs that passed the float prefilter
     int cap;
-    int* counters;  // [0] unresolved, [1] survivors, [2] staged accepts, [3] span of the current wave
+    int* counters;  // [0] unresolved, [1] survivors, [2] staged accepts, [3] span of the current wave, [4] ticket,
+                    // diagnostics: [5] tries prefiltered, [6] survivors judged, [7] waves that had work
     int M;
 };
 // Returns the number of kernel launches it enqueued.
 int launch_sample(const float* coords, float4* coords4, const int* assign32, const Problem& P, uint64_t seed, int max_tries,
                   const int* injected, int inj_T, const SampleState* st, int n_lanes, int sm_count, int use_prefilter,
-                  int hyp_offset, int hyp_stride, Pose* poses, int* cells, int* tries, cudaStream_t stream, cudaStream_t aux,
-                  cudaEvent_t ev_fork, cudaEvent_t ev_join, int split_e, const int* perm, const int* offsets,
-                  const cudaEvent_t* ev_half);
+                  int hyp_offset, int hyp_stride, Pose* poses, int* cells, int* tries, const cudaStream_t* lanes,
+                  cudaEvent_t ev_fork, const cudaEvent_t* ev_join, int split_e, const int* perm, const int* offsets,
+                  const cudaEvent_t* ev_half, int span0, float window, int n_waves,
+                  unsigned long long* trace, float tail_boost);
+void launch_trace_init(unsigned long long* trace, int slots, cudaStream_t st);
 
 // --- refine.cu ----------------------------------------------------------------------------
 // Refines poses_in[jobs[j]] -> poses_out[jobs[j]] for j < *n_jobs (device scalar) or n_jobs_host.

@@ -21,6 +21,8 @@
 //
 // Keeping the float and double paths in different kernels matters: fused, the kernel ran at 10% issue utilisation,
 // stalled on instruction fetch (profiles/r01b_sample_kernel_ncu.json).
+#include <string.h>
+
 #include "esac_internal.h"
 #include "esac_p3p_fast.cuh"
 #include "esac_rng.cuh"
@@ -47,7 +49,25 @@ struct SampleArgs {
     const int* perm;          // ... or, when set, the hypotheses of experts [e_lo, e_hi): perm[offsets[e_lo] + k]
     const int* offsets;
     int e_lo, e_hi;
+    int span0;                // window of the first wave (tries per hypothesis)
+    float window;             // later windows: window / (acceptance rate per try seen in the last wave)
+    float tail_boost;         // ... times this once <= 64 hypotheses are left (twice this for <= 8)
     SampleState st;
+    unsigned long long* trace;  // diagnostics (option sample_trace): [slot][2] first CTA start / last CTA end, globaltimer ns
+    int trace_slot;
+};
+
+__device__ __forceinline__ unsigned long long gtime() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+    return t;
+}
+struct TraceScope {  // thread 0 of every CTA stamps its kernel's slot
+    unsigned long long* p;
+    __device__ TraceScope(const unsigned long long* base, int slot) : p(nullptr) {
+        if (base && threadIdx.x == 0) { p = const_cast<unsigned long long*>(base) + 2 * slot; atomicMin(p, gtime()); }
+    }
+    __device__ ~TraceScope() { if (p) atomicMax(p + 1, gtime()); }
 };
 
 // k-th hypothesis of the lane and the lane's size
@@ -104,11 +124,15 @@ __global__ void sample_init_kernel(const __grid_constant__ SampleArgs a) {
         const int h = lane_hyp(a, k);
         st.best[h] = kNoKey; st.base[h] = 0; st.ovf[h] = kNoTry; st.list[k] = h;
     }
-    if (k == 0) { st.counters[0] = n; st.counters[1] = 0; st.counters[2] = 0; st.counters[3] = 128; st.counters[4] = 0; }  // unresolved, survivors, staged, span, ticket
+    if (k == 0) {  // unresolved, survivors, staged, span, ticket; diagnostics: tries prefiltered, survivors judged, waves with work
+        st.counters[0] = n; st.counters[1] = 0; st.counters[2] = 0; st.counters[3] = a.span0; st.counters[4] = 0;
+        st.counters[5] = 0; st.counters[6] = 0; st.counters[7] = 0;
+    }
 }
 
 // ---- wave phase 1: fp32 prefilter, one thread per try --------------------------------------------------------
 __global__ void __launch_bounds__(kTryThreads, 8) prefilter_kernel(const __grid_constant__ SampleArgs a) {
+    TraceScope trace(a.trace, a.trace_slot);
     const int n_unres = a.st.counters[0];
     const int span = a.st.counters[3];
     const int cph = (span + kTryThreads - 1) / kTryThreads;  // chunks per hypothesis
@@ -142,10 +166,11 @@ __global__ void __launch_bounds__(kTryThreads, 8) prefilter_kernel(const __grid_
     }
 }
 
-__device__ void advance_wave(const SampleState& st, int limit);
+__device__ void advance_wave(const SampleState& st, int limit, float window, float tail_boost);
 
 // ---- wave phase 2: exact fp64 verdict on the survivors -------------------------------------------------------
 __global__ void __launch_bounds__(128) exact_kernel(const __grid_constant__ SampleArgs a) {
+    TraceScope trace(a.trace, a.trace_slot);
     const int n = min(a.st.counters[1], a.st.cap);
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
         const int2 ht = a.st.surv[i];
@@ -174,12 +199,12 @@ __global__ void __launch_bounds__(128) exact_kernel(const __grid_constant__ Samp
     __syncthreads();
     if (s_last) {
         __threadfence();
-        advance_wave(a.st, a.limit);
+        advance_wave(a.st, a.limit, a.window, a.tail_boost);
     }
 }
 
 // ---- wave phase 3: bookkeeping (run by the last CTA of exact_kernel to finish) -------------------------------------
-__device__ void advance_wave(const SampleState& st, int limit) {
+__device__ void advance_wave(const SampleState& st, int limit, float window, float tail_boost) {
     __shared__ int s_fill;
     const int span = st.counters[3];
     if (threadIdx.x == 0) s_fill = 0;
@@ -206,14 +231,22 @@ __device__ void advance_wave(const SampleState& st, int limit) {
     __syncthreads();
     if (threadIdx.x == 0) {
         // next window: ~1.25 / (acceptance rate per try seen in this wave), a multiple of the CTA size
+        const int n_surv = min(st.counters[1], st.cap);
         const double tried = (double)n_unres * (double)span;
         const double hits = n_unres - nn > 0 ? (double)(n_unres - nn) : 0.5;
-        double next_span = 1.25 * tried / hits;
+        // few hypotheses left: their tries cost next to nothing, a further wave costs a full verdict latency -- ask for more
+        const double boost = nn <= 8 ? tail_boost * 2. : (nn <= 64 ? tail_boost : 1.);
+        double next_span = (double)window * boost * tried / hits;
         next_span = next_span < 128. ? 128. : (next_span > 65536. ? 65536. : next_span);
         st.counters[3] = ((int)next_span + kTryThreads - 1) / kTryThreads * kTryThreads;
         st.counters[0] = nn;
         st.counters[1] = 0;
         st.counters[4] = 0;  // ticket of the next exact_kernel
+        if (n_unres > 0) {
+            st.counters[5] += n_unres * span;
+            st.counters[6] += n_surv;
+            st.counters[7] += 1;
+        }
     }
 }
 
@@ -253,6 +286,7 @@ __global__ void __launch_bounds__(kTryThreads) tail_kernel(const __grid_constant
     }
 }
 
+
 // ---- emit: pose / cells / try count of every hypothesis ------------------------------------------------------
 __global__ void __launch_bounds__(64) emit_kernel(const __grid_constant__ SampleArgs a, Pose* poses, int* cells, int* tries) {
     const int k = blockIdx.x * blockDim.x + threadIdx.x;
@@ -277,58 +311,78 @@ __global__ void __launch_bounds__(64) emit_kernel(const __grid_constant__ Sample
     tries[h] = t + 1;
 }
 
-// The hypotheses are dealt to n_lanes (<= 2) lanes, each with its own work list, survivor list, staging area and stream.
+// The hypotheses are dealt to n_lanes lanes, each with its own work list, survivor list, staging area and stream.
 // A wave is a throughput-bound kernel (prefilter) followed by a latency-bound one (exact: a few thousand threads, each a
-// long fp64 dependency chain); with two lanes in flight the exact kernel of one runs under the prefilter of the other
+// ~25 us fp64 dependency chain); with two lanes in flight the exact kernel of one can run under the prefilter of the other
 // instead of leaving the GPU idle.  Lanes are dealt by hypothesis parity, or -- when the coordinate maps are still
 // arriving from the host in two halves (split_e > 0) -- by expert: lane 0 = experts [0, split_e), released by
 // ev_half[0]; lane 1 = the rest, released by ev_half[1], so lane 0 samples while the second half is on the wire.
+// What was tried on top of this and measured slower or equal (profiles/r02h_*.txt): 3-4 lanes, one
+// prefilter stream + per-lane verdict streams in forced anti-phase, other window policies, a single persistent kernel with
+// work / survivor queues.  option sample_trace shows who runs when.
 int launch_sample(const float* coords, float4* coords4, const int* assign32, const Problem& P, uint64_t seed, int max_tries,
                   const int* injected, int inj_T, const SampleState* st, int n_lanes, int sm_count, int use_prefilter,
-                  int hyp_offset, int hyp_stride, Pose* poses, int* cells, int* tries, cudaStream_t stream, cudaStream_t aux,
-                  cudaEvent_t ev_fork, cudaEvent_t ev_join, int split_e, const int* perm, const int* offsets,
-                  const cudaEvent_t* ev_half) {
+                  int hyp_offset, int hyp_stride, Pose* poses, int* cells, int* tries, const cudaStream_t* lanes,
+                  cudaEvent_t ev_fork, const cudaEvent_t* ev_join, int split_e, const int* perm, const int* offsets,
+                  const cudaEvent_t* ev_half, int span0, float window, int n_waves,
+                  unsigned long long* trace, float tail_boost) {
     int launches = 0;
+    cudaStream_t stream = lanes[0];
     if (!split_e) { interleave_kernel<<<sm_count * 8, 256, 0, stream>>>(coords, coords4, P.E, P.N); ++launches; }
-    if (n_lanes > 1) {
-        cudaEventRecord(ev_fork, stream);
-        cudaStreamWaitEvent(aux, ev_fork, 0);
-    }
+    SampleArgs args[4];
+    int bound[4];
     for (int g = 0; g < n_lanes; ++g) {
-        cudaStream_t sg = g == 0 ? stream : aux;
-        SampleArgs a;
+        SampleArgs& a = args[g];
         a.coords4 = coords4; a.assign32 = assign32; a.P = P; a.seed = seed;
         a.limit = injected ? (max_tries < inj_T ? max_tries : inj_T) : max_tries;
         a.injected = injected; a.inj_T = inj_T; a.st = st[g]; a.use_prefilter = use_prefilter; a.hyp_offset = hyp_offset; a.hyp_stride = hyp_stride > 0 ? hyp_stride : 1;
         a.h_first = g; a.h_step = n_lanes; a.Mg = (P.M - g + n_lanes - 1) / n_lanes;
         a.perm = nullptr; a.offsets = nullptr; a.e_lo = a.e_hi = 0;
-        int bound = a.Mg;  // host-side bound on the lane size (grid sizing)
+        a.span0 = span0; a.window = window; a.trace = trace; a.trace_slot = 0; a.tail_boost = tail_boost;
+        bound[g] = a.Mg;  // host-side bound on the lane size (grid sizing)
         if (split_e) {
             a.perm = perm; a.offsets = offsets;
             a.e_lo = g == 0 ? 0 : split_e;
             a.e_hi = g == 0 ? split_e : P.E;
-            bound = P.M;
+            bound[g] = P.M;
+        }
+    }
+    if (n_lanes > 1) {
+        cudaEventRecord(ev_fork, stream);
+        for (int g = 1; g < n_lanes; ++g) cudaStreamWaitEvent(lanes[g], ev_fork, 0);
+    }
+    for (int g = 0; g < n_lanes; ++g) {
+        cudaStream_t sg = lanes[g];
+        SampleArgs& a = args[g];
+        if (split_e) {
             cudaStreamWaitEvent(sg, ev_half[g], 0);
             const int ne = a.e_hi - a.e_lo;
             interleave_kernel<<<sm_count * 8, 256, 0, sg>>>(coords + (size_t)a.e_lo * 3 * P.N, coords4 + (size_t)a.e_lo * P.N, ne, P.N);
             ++launches;
         }
-        if (bound <= 0) continue;
-        sample_init_kernel<<<(bound + 255) / 256, 256, 0, sg>>>(a); ++launches;
-        const int kWaves = 7;
+        if (bound[g] <= 0) continue;
+        sample_init_kernel<<<(bound[g] + 255) / 256, 256, 0, sg>>>(a); ++launches;
         const int grid = sm_count * 16;
-        for (int r = 0; r < kWaves; ++r) {
+        for (int r = 0; r < n_waves; ++r) {
+            a.trace_slot = (g * 32 + r) * 2;
             prefilter_kernel<<<grid, kTryThreads, 0, sg>>>(a); ++launches;
+            a.trace_slot = (g * 32 + r) * 2 + 1;
             exact_kernel<<<sm_count * 4, 128, 0, sg>>>(a); ++launches;  // its last CTA also advances the windows
         }
-        tail_kernel<<<bound < sm_count * 4 ? bound : sm_count * 4, kTryThreads, 0, sg>>>(a); ++launches;
-        emit_kernel<<<(bound + 63) / 64, 64, 0, sg>>>(a, poses, cells, tries); ++launches;
+        tail_kernel<<<bound[g] < sm_count * 4 ? bound[g] : sm_count * 4, kTryThreads, 0, sg>>>(a); ++launches;
+        emit_kernel<<<(bound[g] + 63) / 64, 64, 0, sg>>>(a, poses, cells, tries); ++launches;
     }
-    if (n_lanes > 1) {
-        cudaEventRecord(ev_join, aux);
-        cudaStreamWaitEvent(stream, ev_join, 0);
+    for (int g = 1; g < n_lanes; ++g) {
+        cudaEventRecord(ev_join[g], lanes[g]);
+        cudaStreamWaitEvent(stream, ev_join[g], 0);
     }
     return launches;
 }
+
+__global__ void trace_init_kernel(unsigned long long* trace, int slots) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < slots) { trace[2 * i] = ~0ull; trace[2 * i + 1] = 0ull; }
+}
+void launch_trace_init(unsigned long long* trace, int slots, cudaStream_t st) { trace_init_kernel<<<(slots + 255) / 256, 256, 0, st>>>(trace, slots); }
 
 }  // namespace esacb200

@@ -215,6 +215,14 @@ int esacb200_get_stats(esacb200_ctx* ctx, esacb200_stats* out);
  * out16: host long long [16]. */
 int esacb200_get_refine_profile(esacb200_ctx* ctx, long long* out16);
 
+/* Diagnostics of the last call's sampling stage (summed over its lanes): [0] tries that went through the float prefilter,
+ * [1] survivors the fp64 path judged, [2] waves that had work (max over lanes), [3] hypotheses left to the tail kernel,
+ * [4] accepted tries staged, [5] lanes.  out8: host long long [8]. */
+int esacb200_get_sample_profile(esacb200_ctx* ctx, long long* out8);
+/* With option "sample_trace" = 1 the prefilter / exact kernels of the sampling waves stamp %globaltimer: out512 (host uint64
+ * [4 lanes][32 waves][2 kernels: prefilter, exact][2: first CTA start, last CTA end], ns; start = ~0 where nothing ran). */
+int esacb200_get_sample_trace(esacb200_ctx* ctx, unsigned long long* out512);
+
 /* Read back intermediates of the last forward/backward call (any pointer may be NULL):
  * poses6 double [M][6] initial hypotheses, cells int32 [M][4][2], tries int32 [M], scores / probs double [M],
  * refined6 double [M][6] (backward: refined poses; forward: only the winner's row is meaningful),

@@ -53,7 +53,7 @@ def test_forward_and_backward_match_the_compiled_reference(api, path):
     if "grads" in z.files:
         scale = max(np.abs(z["grads"]).max(), 1e-12)
         assert np.abs(g - z["grads"]).max() / scale < 1e-3
-        if "unclamped_grad_diff" in z.files and len(z["clamped_jr"]) + len(z["clamped_dpnp"]):
+        if "unclamped_grad_diff" in z.files and "_off_" not in path.stem:
             # clamp fixtures (esac.cpp:436-437, esac_derivative.h:287): without the `> 10` clamps the gradient would sit this
             # far away (tests/test_oracle.py::test_clamp_fixtures_really_trip_the_clamps), i.e. >= 50 tolerances
             assert float(z["unclamped_grad_diff"]) / scale > 0.05
