@@ -71,6 +71,7 @@ struct esacb200_ctx {
     int max_ref_steps = 100;
     int fixed_seed = 0;
     int refine_group_opt = 0;
+    int refine_compact = 1;    // LM evaluations over per-CTA inlier lists instead of predicated passes over all cells
     int refine_profile = 0;    // 1: block 0 of the refinement kernel records phase cycle counts (esacb200_get_refine_profile)
     int refine_jobs_per_group = 3;
     int sample_prefilter = 1;
@@ -88,7 +89,7 @@ struct esacb200_ctx {
     // workspace
     DevBuf coords, grads, assign64, assign32, counts, offsets, perm, slot_of, chunks, scalars, centres, poses, poses_ref,
         cells, tries, posepk, part, scores, probs, stats, contrib, masks, rounds, scratch, barrier, out17, inject,
-        losses, red, hypgrad, job_of, gt, smp_int, smp_surv, smp_trace, coords4, coords_alt, assign64_alt, out_batch, prof;
+        losses, red, hypgrad, job_of, gt, smp_int, smp_surv, smp_trace, clist, coords4, coords_alt, assign64_alt, out_batch, prof;
     float* h_out = nullptr;  // pinned staging: 32 floats
     double* h_dbl = nullptr; // pinned staging: 8 doubles
     int inj_M = 0, inj_T = 0;
@@ -473,7 +474,14 @@ int run_refine(esacb200_ctx* ctx, const Plan& pl, const Pose* in, Pose* out, con
     a.barrier = ctx->barrier.as<unsigned int>();
     a.job_counter = (int*)(ctx->barrier.as<unsigned int>() + n_flags);
     a.group = group;
-    a.cache = ((words + group - 1) / group) <= refine_cache_words() ? 1 : 0;
+    const int wpc = (words + group - 1) / group;
+    a.cache = wpc <= refine_cache_words() ? 1 : 0;
+    a.compact = ctx->refine_compact;
+    a.clist = nullptr;
+    if (a.compact && !a.cache && wpc <= refine_max_compact_words()) {
+        CK(ctx->clist.ensure((size_t)n_groups * words * 32 * sizeof(unsigned short)));
+        a.clist = ctx->clist.as<unsigned short>();
+    }
     a.prof = nullptr;
     if (ctx->refine_profile) {
         CK(ctx->prof.ensure(16 * 8));
@@ -605,7 +613,7 @@ void esacb200_destroy(esacb200_ctx* ctx) {
                       &ctx->slot_of, &ctx->chunks, &ctx->scalars, &ctx->centres, &ctx->poses, &ctx->poses_ref, &ctx->cells,
                       &ctx->tries, &ctx->posepk, &ctx->part, &ctx->scores, &ctx->probs, &ctx->stats, &ctx->contrib,
                       &ctx->masks, &ctx->rounds, &ctx->scratch, &ctx->barrier, &ctx->out17, &ctx->inject, &ctx->losses,
-                      &ctx->red, &ctx->hypgrad, &ctx->job_of, &ctx->gt, &ctx->smp_int, &ctx->smp_surv, &ctx->smp_trace, &ctx->coords4, &ctx->coords_alt, &ctx->assign64_alt, &ctx->out_batch, &ctx->prof, &ctx->gathered, &ctx->grads_work};
+                      &ctx->red, &ctx->hypgrad, &ctx->job_of, &ctx->gt, &ctx->smp_int, &ctx->smp_surv, &ctx->smp_trace, &ctx->clist, &ctx->coords4, &ctx->coords_alt, &ctx->assign64_alt, &ctx->out_batch, &ctx->prof, &ctx->gathered, &ctx->grads_work};
     for (DevBuf* b : bufs) b->release();
     for (int i = 0; i < EV_COUNT; ++i)
         if (ctx->ev[i]) cudaEventDestroy(ctx->ev[i]);
@@ -648,6 +656,7 @@ int esacb200_set_option(esacb200_ctx* ctx, const char* key, double v) {
     else if (!strcmp(key, "max_ref_steps")) ctx->max_ref_steps = v < 0 ? 0 : (int)v;
     else if (!strcmp(key, "fixed_seed")) ctx->fixed_seed = v != 0;
     else if (!strcmp(key, "refine_group")) ctx->refine_group_opt = (int)v;
+    else if (!strcmp(key, "refine_compact")) ctx->refine_compact = v != 0;
     else if (!strcmp(key, "refine_profile")) ctx->refine_profile = v != 0;
     else if (!strcmp(key, "refine_jobs_per_group")) ctx->refine_jobs_per_group = v < 1 ? 1 : (int)v;
     else if (!strcmp(key, "sample_prefilter")) ctx->sample_prefilter = v != 0;
@@ -1272,6 +1281,7 @@ int esacb200_backward_batch(esacb200_ctx* ctx, int B, const float* coords, float
         w->max_ref_steps = ctx->max_ref_steps;
         w->refine_group_opt = ctx->refine_group_opt;
         w->refine_jobs_per_group = ctx->refine_jobs_per_group;
+        w->refine_compact = ctx->refine_compact;
         w->sample_prefilter = ctx->sample_prefilter;
         w->sample_tail_boost = ctx->sample_tail_boost;
         w->hyp_offset = ctx->hyp_offset;

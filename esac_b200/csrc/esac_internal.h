@@ -139,6 +139,8 @@ struct RefineArgs {
     int* job_counter;        // next job to hand out (dynamic scheduling), zeroed before launch
     int group;               // CTAs cooperating on one job
     int cache;               // 1: every CTA's share of the map fits the shared-memory cell cache
+    int compact;             // 1: LM evaluations walk a per-CTA list of the round's inlier cells
+    unsigned short* clist;   // [n_groups][words * 32] inlier lists of blocks whose share does not fit shared memory (or null)
     long long* prof;         // diagnostics: 16 cycle counters of block 0 (null = off)
     Problem P;
     int max_ref_steps;
@@ -146,6 +148,7 @@ struct RefineArgs {
 void launch_refine(const RefineArgs& a, int n_groups, cudaStream_t st);
 int refine_max_coresident_blocks(int sm_count);
 int refine_cache_words();
+int refine_max_compact_words();
 size_t refine_scratch_doubles(int n_groups, int group);
 size_t refine_flag_words(int n_groups, int group);
 // camera->world 4x4 float of poses[*winner] packed for one D2H copy: out[0..15], out[16] = expert id,

@@ -37,7 +37,13 @@ constexpr int kSlot = 32;   // doubles per CTA slot / per command record
 // coordinates never change between evaluations): 96 words = 3072 cells = 36 KB.  Forward at 480x640 on 148 CTAs: 65 words.
 constexpr int kCacheWords = 96;
 constexpr int kCacheCells = kCacheWords * 32;
+// Inlier compaction: after the pass that selects a round's inliers every CTA lists the inlier cells of its share (16-bit
+// offsets from its first cell), and the round's LM evaluations walk that list with every lane busy instead of walking all
+// cells with the outliers' lanes predicated off -- an fp64 instruction costs the same issue slot however many lanes are on.
+// Up to this many 32-cell words per CTA (offsets must fit 16 bits; the popcounts live in shared memory):
+constexpr int kMaxCompactWords = 2048;
 
+size_t refine_cache_bytes();
 enum { CMD_EVAL = 1, CMD_FIRST = 2, CMD_EXIT = 3 };
 // command record (doubles): [0..5] parameters (rvec, tvec), [6..14] R, [15..17] t = R c + tvec, [18] command, [19] job,
 // [20] mask buffer the round's tentative inlier set lives in
@@ -54,6 +60,9 @@ struct RefShared {
     double Rc[3], dR[27], T[9], G[36], H1[36];
     double prev_cost, best;
     int lamlg, iters, mode, rounds, sel, step, job, h, finished;
+    int n_list;                    // inlier cells of this CTA's share in the current round (compaction)
+    int wsum[kRefWarps];
+    int cnt[kMaxCompactWords];     // per word: popcount, then exclusive prefix
     long long prof_last;  // diagnostics (a.prof != null): clock of the previous phase boundary, thread 0 of block 0
 };
 
@@ -193,7 +202,7 @@ __device__ __forceinline__ void accumulate_normal(double a_, double c_, double d
 template <bool BUILD_MASK, bool CACHED>
 __device__ __forceinline__ void lm_accumulate(const float* __restrict__ pl, const float* __restrict__ cache, const Problem& P,
                                               const double* R, const double* t, const double* c, uint32_t* mask, int w0, int w1,
-                                              const double* t0, double (&acc)[kRedN + 1]) {
+                                              const double* t0, double (&acc)[kRedN + 1], int* cnt) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 #pragma unroll
     for (int i = 0; i < kRedN + 1; ++i) acc[i] = 0;
@@ -215,7 +224,11 @@ __device__ __forceinline__ void lm_accumulate(const float* __restrict__ pl, cons
                 inl = err < P.tau;                                  // esac_util.h:406
             }
             const uint32_t bits = __ballot_sync(0xffffffffu, inl);
-            if (lane == 0) { mask[w] = bits; acc[kRedN] += (double)__popc(bits); }
+            if (lane == 0) {
+                mask[w] = bits;
+                acc[kRedN] += (double)__popc(bits);
+                if (cnt) cnt[w - w0] = __popc(bits);
+            }
         } else {
             inl = (mask[w] >> lane) & 1u;
             if (inl) {
@@ -238,6 +251,65 @@ __device__ __forceinline__ void lm_accumulate(const float* __restrict__ pl, cons
             accumulate_normal(a_, c_, d_, qx, qy, qz, ru, rv, acc);
         }
     }
+}
+
+// The same sums over the listed inlier cells only (list[i] = cell offset from the share's first cell).
+template <bool CACHED>
+__device__ __forceinline__ void lm_accumulate_list(const float* __restrict__ pl, const float* __restrict__ cache, const Problem& P,
+                                                   const double* R, const double* t, const double* c, const unsigned short* list,
+                                                   int n, int w0, double (&acc)[kRedN + 1]) {
+#pragma unroll
+    for (int i = 0; i < kRedN + 1; ++i) acc[i] = 0;
+    const double f = (double)P.f, cx = (double)P.ppx, cy = (double)P.ppy;
+    for (int i = threadIdx.x; i < n; i += kRefThreads) {
+        const int lc = list[i];
+        const int p = w0 * 32 + lc;
+        const int yy = p / P.W, xx = p - yy * P.W;
+        const double px = (double)(xx * P.sub + P.sub / 2 - P.shiftX), py = (double)(yy * P.sub + P.sub / 2 - P.shiftY);
+        float Xf, Yf, Zf;
+        if (CACHED) { Xf = cache[lc]; Yf = cache[kCacheCells + lc]; Zf = cache[2 * kCacheCells + lc]; }
+        else { Xf = pl[p]; Yf = pl[P.N + p]; Zf = pl[2 * (size_t)P.N + p]; }
+        const double X = (double)Xf - c[0], Y = (double)Yf - c[1], Z = (double)Zf - c[2];
+        const double qx = R[0] * X + R[1] * Y + R[2] * Z;
+        const double qy = R[3] * X + R[4] * Y + R[5] * Z;
+        const double qz = R[6] * X + R[7] * Y + R[8] * Z;
+        const double zc = qz + t[2];
+        const double iz = zc != 0. ? 1. / zc : 1.;
+        const double xn = (qx + t[0]) * iz, yn = (qy + t[1]) * iz;
+        const double ru = xn * f + cx - px, rv = yn * f + cy - py;
+        const double a_ = f * iz, c_ = -f * xn * iz, d_ = -f * yn * iz;
+        acc[27] += ru * ru + rv * rv;
+        accumulate_normal(a_, c_, d_, qx, qy, qz, ru, rv, acc);
+    }
+}
+
+// Builds the CTA's inlier list from the mask words the selection pass just wrote (sh.cnt holds their popcounts): exclusive
+// prefix over the words, then every set bit writes its offset.  Fixed order, so the sums stay reproducible run to run.
+__device__ __forceinline__ void build_inlier_list(RefShared& sh, const uint32_t* mask, int w0, int w1, unsigned short* list) {
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int nw = w1 - w0;
+    __syncthreads();  // popcounts of every warp are in
+    int v[4], s = 0;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) { const int i = tid * 4 + k; v[k] = i < nw ? sh.cnt[i] : 0; s += v[k]; }
+    int inc = s;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { const int x = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += x; }
+    if (lane == 31) sh.wsum[warp] = inc;
+    __syncthreads();
+    int base = 0;
+#pragma unroll
+    for (int w = 0; w < kRefWarps; ++w) base += w < warp ? sh.wsum[w] : 0;
+    int run = base + inc - s;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) { const int i = tid * 4 + k; if (i < nw) sh.cnt[i] = run; run += v[k]; }
+    if (tid == kRefThreads - 1) sh.n_list = run;
+    __syncthreads();
+    for (int w = w0 + warp; w < w1; w += kRefWarps) {
+        const uint32_t bits = mask[w];
+        if ((bits >> lane) & 1u) list[sh.cnt[w - w0] + __popc(bits & ((1u << lane) - 1u))] = (unsigned short)((w - w0) * 32 + lane);
+    }
+    __syncthreads();
 }
 
 // 6x6 SPD solve on one thread by 3x3 block elimination with closed-form (adjugate) 3x3 inverses: two reciprocals and a
@@ -457,7 +529,7 @@ __device__ __forceinline__ void root_lm_step(RefShared& sh) {
 
 __global__ void __launch_bounds__(kRefThreads, 1) refine_kernel(const __grid_constant__ RefineArgs a) {
     __shared__ RefShared sh;
-    extern __shared__ float cell_cache[];  // [3][kCacheCells] when the block's share fits (a.cache != 0)
+    extern __shared__ float cell_cache[];  // [3][kCacheCells] + the inlier list when the block's share fits (a.cache != 0)
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int n_groups = gridDim.x / a.group;
     const int grp = blockIdx.x / a.group, cta = blockIdx.x - grp * a.group;
@@ -469,6 +541,10 @@ __global__ void __launch_bounds__(kRefThreads, 1) refine_kernel(const __grid_con
     const int w0 = min(words, cta * wpc), w1 = min(words, w0 + wpc);
     const bool cached = a.cache != 0;
     const bool dynamic = n_groups < n_jobs;
+    // inlier list of this CTA's share: behind the cell cache in shared memory, else in the group's global scratch
+    const bool compact = a.compact && (w1 - w0) <= kMaxCompactWords && (cached || a.clist);
+    unsigned short* list = cached ? reinterpret_cast<unsigned short*>(cell_cache + 3 * kCacheCells)
+                                  : (a.clist ? a.clist + (size_t)grp * words * 32 + (size_t)w0 * 32 : nullptr);
     unsigned seq = 0;  // sequence number of the current command / result exchange (same in every block of the group)
     int cur_job = -1, cached_expert = -1;
     const float* pl = nullptr;
@@ -575,14 +651,20 @@ __global__ void __launch_bounds__(kRefThreads, 1) refine_kernel(const __grid_con
         const double* t = sh.cmd + C_T;
         const double* t0 = sh.cmd + C_PAR + 3;
         if (cmd == CMD_FIRST) {
-            if (cached) lm_accumulate<true, true>(pl, cell_cache, P, R, t, cen, mtent, w0, w1, t0, acc);
-            else lm_accumulate<true, false>(pl, cell_cache, P, R, t, cen, mtent, w0, w1, t0, acc);
+            int* cnt = compact ? sh.cnt : nullptr;
+            if (cached) lm_accumulate<true, true>(pl, cell_cache, P, R, t, cen, mtent, w0, w1, t0, acc, cnt);
+            else lm_accumulate<true, false>(pl, cell_cache, P, R, t, cen, mtent, w0, w1, t0, acc, cnt);
+        } else if (compact) {
+            if (cached) lm_accumulate_list<true>(pl, cell_cache, P, R, t, cen, list, sh.n_list, w0, acc);
+            else lm_accumulate_list<false>(pl, cell_cache, P, R, t, cen, list, sh.n_list, w0, acc);
         } else {
-            if (cached) lm_accumulate<false, true>(pl, cell_cache, P, R, t, cen, mtent, w0, w1, t0, acc);
-            else lm_accumulate<false, false>(pl, cell_cache, P, R, t, cen, mtent, w0, w1, t0, acc);
+            if (cached) lm_accumulate<false, true>(pl, cell_cache, P, R, t, cen, mtent, w0, w1, t0, acc, nullptr);
+            else lm_accumulate<false, false>(pl, cell_cache, P, R, t, cen, mtent, w0, w1, t0, acc, nullptr);
         }
         tick(a, sh, 1);
         block_reduce_publish<kRedN + 1>(acc, sh, a, grp, cta, seq);
+        // the round's inlier list, after this block's totals are out (the other blocks build theirs while the root decides)
+        if (cmd == CMD_FIRST && compact) build_inlier_list(sh, mtent, w0, w1, list);
         tick(a, sh, 2);
         if (!root) continue;
         // ================= root: gather, decide, step =================
@@ -661,20 +743,25 @@ __global__ void __launch_bounds__(kRefThreads, 1) refine_kernel(const __grid_con
 
 void launch_refine(const RefineArgs& a, int n_groups, cudaStream_t st) {
     dim3 grid(n_groups * a.group), block(kRefThreads);
-    const size_t smem = a.cache ? (size_t)3 * kCacheCells * sizeof(float) : 0;
+    const size_t smem = a.cache ? refine_cache_bytes() : 0;
     void* params[] = {(void*)&a};
+    // above the 48 KB a kernel gets without asking; the attribute is per device, so it is set on every launch (it is cheap)
+    cudaFuncSetAttribute((const void*)refine_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)refine_cache_bytes());
     if (a.group > 1) cudaLaunchCooperativeKernel((const void*)refine_kernel, grid, block, params, smem, st);
     else cudaLaunchKernel((const void*)refine_kernel, grid, block, params, smem, st);
 }
 
 int refine_cache_words() { return kCacheWords; }
+size_t refine_cache_bytes() { return (size_t)3 * kCacheCells * sizeof(float) + (size_t)kCacheCells * sizeof(unsigned short); }
+int refine_max_compact_words() { return kMaxCompactWords; }
 // scratch doubles / flag words a launch of n_groups x group blocks needs
 size_t refine_scratch_doubles(int n_groups, int group) { return (size_t)n_groups * (group + 2) * 2 * kSlot; }
 size_t refine_flag_words(int n_groups, int group) { return (size_t)n_groups * (group + 1); }
 
 int refine_max_coresident_blocks(int sm_count) {
     int nb = 0;
-    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, refine_kernel, kRefThreads, (size_t)3 * kCacheCells * sizeof(float)) != cudaSuccess) {
+    cudaFuncSetAttribute((const void*)refine_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)refine_cache_bytes());
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, refine_kernel, kRefThreads, refine_cache_bytes()) != cudaSuccess) {
         cudaGetLastError();
         nb = 1;
     }

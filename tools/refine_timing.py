@@ -15,7 +15,8 @@ for name, sc in (("full 7x256 480x640", full), ("native 60x80 M=256", nat)):
     coords = torch.from_numpy(sc.coords).cuda(); assign = torch.from_numpy(sc.assign).cuda()
     out = torch.zeros(4, 4, device="cuda")
     ref = None
-    for mixed in (0,):
+    for mixed in (0, 1):  # inlier compaction off / on
+        ctx.set_option("refine_compact", mixed)
         ts, rs = [], []
         for i in range(6):
             ctx.set_seed(100 + i)
@@ -27,14 +28,15 @@ for name, sc in (("full 7x256 480x640", full), ("native 60x80 M=256", nat)):
         if ref is None:
             ref = p
         d = pose_error(p, ref)
-        print(f"fwd {name}: mixed={mixed} refine ms {np.round(ts, 3).tolist()} rounds {rs} group {st['refine_group']} "
-              f"total {st['ms_total']:.3f} pose diff vs fp64 {d[0]:.2e} deg {d[1]:.2e} m", flush=True)
+        print(f"fwd {name}: compact={mixed} refine ms {np.round(ts, 3).tolist()} rounds {rs} group {st['refine_group']} "
+              f"total {st['ms_total']:.3f} pose diff vs uncompacted {d[0]:.2e} deg {d[1]:.2e} m", flush=True)
 for name, sc in (("full 7x256 480x640", full), ("c5 20E M=1024 480x640", c5), ("native 60x80 M=256", nat)):
     coords = torch.from_numpy(sc.coords).cuda(); assign = torch.from_numpy(sc.assign).cuda()
     gt = torch.from_numpy(sc.gt_pose)
     grads = torch.zeros_like(coords)
     base = None
-    for mixed, jpg, grp in ((0, 1, 0), (0, 2, 0), (0, 3, 0), (0, 4, 0), (0, 6, 0), (0, 3, 1), (0, 3, 2), (0, 3, 16)):
+    for mixed, jpg, grp in ((0, 3, 0), (1, 3, 0), (1, 2, 0), (1, 4, 0), (1, 6, 0), (1, 3, 16), (1, 3, 32)):
+        ctx.set_option("refine_compact", mixed)
         ctx.set_option("refine_jobs_per_group", jpg); ctx.set_option("refine_group", grp)
         ts = []
         for i in range(4):
@@ -46,6 +48,6 @@ for name, sc in (("full 7x256 480x640", full), ("c5 20E M=1024 480x640", c5), ("
         if base is None:
             base = (loss, g)
         dg = np.abs(g - base[1]).max() / max(np.abs(base[1]).max(), 1e-30)
-        print(f"bwd {name}: mixed={mixed} jobs/group={jpg} group_opt={grp} -> group {st['refine_group']} contrib {st['n_contrib']} "
+        print(f"bwd {name}: compact={mixed} jobs/group={jpg} group_opt={grp} -> group {st['refine_group']} contrib {st['n_contrib']} "
               f"refine ms {np.round(ts[1:], 3).tolist()} total {st['ms_total']:.3f} loss diff {abs(loss - base[0]):.2e} grad rel diff {dg:.2e}", flush=True)
     ctx.set_option("refine_group", 0); ctx.set_option("refine_jobs_per_group", 3)
