@@ -205,6 +205,19 @@ def run_configs(rank: int, world: int, dev, api, sharded, dist, reps: int = 4):
             ms = float(t.item())
         return ms
 
+    def rank_stages():
+        """The library's CUDA-event stage timers of this rank's LAST call, as lists over the ranks (ms)."""
+        keys = ["ms_sample", "ms_score", "ms_select", "ms_refine", "ms_backward", "ms_total"]
+        st = api.context(dev.index).stats()
+        t = torch.tensor([st[k] for k in keys], device=dev, dtype=torch.float64)
+        if world > 1:
+            g = torch.empty(world * len(keys), device=dev, dtype=torch.float64)
+            dist.all_gather_into_tensor(g, t)
+            g = g.view(world, len(keys)).cpu().numpy()
+        else:
+            g = t.view(1, -1).cpu().numpy()
+        return {k: [round(float(v), 4) for v in g[:, i]] for i, k in enumerate(keys)}
+
     # ---- c3 ----
     B = 8
     if B % world == 0:
@@ -233,7 +246,7 @@ def run_configs(rank: int, world: int, dev, api, sharded, dist, reps: int = 4):
         fn = lambda: sharded.forward_sharded(c_l, a_l, pose, sc.params, expert_offset=e0, hyp_offset=e0 * M4, M_pad=M_pad)
     ms = timed(fn, reps)
     out["c4_10experts_512hyp_each_one_image"] = {"value": E4 * M4 / (ms * 1e-3), "unit": UNIT, "ms_per_image": ms, "hyps_per_image": E4 * M4,
-                                                 "experts_per_rank": sizes, "scaling": "strong",
+                                                 "experts_per_rank": sizes, "scaling": "strong", "stages_ms_by_rank": rank_stages(),
                                                  "parallelism": "single GPU" if world == 1 else "expert-major shard, 1 ncclAllGather"}
     del c_l, a_l
     # ---- c5 ----
@@ -258,11 +271,14 @@ def run_configs(rank: int, world: int, dev, api, sharded, dist, reps: int = 4):
         f_bwd = lambda: sharded.backward_sharded(c_l, g_l, a_l, gt, 1.0, 100.0, 100.0, sc.params, hyp_offset=rank, hyp_stride=world,
                                                  reduce_grads=True)
     ms_f = timed(f_fwd, reps)
+    st_f = rank_stages()
     ms_b = timed(f_bwd, reps)
+    st_b = rank_stages()
     st = api.context(dev.index).stats()
     out["c5_20experts_1024hyp_forward_backward"] = {
         "value": M5 / ((ms_f + ms_b) * 1e-3), "unit": UNIT, "ms_forward": ms_f, "ms_backward": ms_b, "hyps_per_image": M5,
         "hyps_per_rank": counts, "contributing_hypotheses_rank0": st["n_contrib"], "scaling": "strong",
+        "stages_ms_by_rank_forward": st_f, "stages_ms_by_rank_backward": st_b,
         "parallelism": "single GPU" if world == 1 else "hypothesis-major shard (all planes on every rank, hypotheses dealt round-robin); forward: "
                        "1 ncclAllGather; backward: ncclAllGather of (max, sum exp) + ncclAllReduce of the expectation + "
                        "ncclAllReduce of the 74 MB gradient tensor",

@@ -455,6 +455,7 @@ int run_refine(esacb200_ctx* ctx, const Plan& pl, const Pose* in, Pose* out, con
     CK(ctx->masks.ensure((size_t)max_jobs * 2 * words * 4));
     CK(ctx->rounds.ensure((size_t)max_jobs * 2 * 4));
     CK(ctx->scratch.ensure(refine_scratch_doubles(n_groups, group) * 8));
+    if (group > 1) CK(cudaMemsetAsync(ctx->scratch.p, 0, refine_scratch_doubles(n_groups, group) * 8, ctx->stream));  // LL elements: no stale sequence numbers
     const size_t n_flags = refine_flag_words(n_groups, group);
     CK(ctx->barrier.ensure((n_flags + 4) * 4));
     CK(cudaMemsetAsync(ctx->barrier.p, 0, (n_flags + 4) * 4, ctx->stream));

@@ -74,6 +74,27 @@ __device__ __forceinline__ unsigned ld_acquire(const unsigned* p) {
 __device__ __forceinline__ void st_release(unsigned* p, unsigned v) {
     asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
+// LL exchange element (the protocol NCCL uses for small messages): a double travels as two 8-byte words, each carrying half of
+// the value and the exchange's sequence number.  A reader that finds the expected number in BOTH words has the whole value, so
+// data and "it is there" arrive in ONE L2 round trip and the writer needs no release fence; buffers are zeroed before a launch
+// and sequence numbers start at 1, so a stale element never matches.
+__device__ __forceinline__ void st_ll(uint4* p, double v, unsigned seq) {
+    const unsigned long long b = (unsigned long long)__double_as_longlong(v);
+    asm volatile("st.volatile.global.v4.u32 [%0], {%1, %2, %3, %4};" ::"l"(p), "r"((unsigned)b), "r"(seq), "r"((unsigned)(b >> 32)), "r"(seq) : "memory");
+}
+__device__ __forceinline__ bool ld_ll(const uint4* p, unsigned seq, double& v) {
+    uint4 w;
+    asm volatile("ld.volatile.global.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(w.x), "=r"(w.y), "=r"(w.z), "=r"(w.w) : "l"(p) : "memory");
+    v = __longlong_as_double((long long)(((unsigned long long)w.z << 32) | w.x));
+    return w.y == seq && w.w == seq;
+}
+// Exchange buffers of a group (uint4 elements): results [block][parity][kSlot], then mailboxes [block][parity][kSlot] -- the
+// root writes every block its OWN copy of a command, so a block polls lines nobody else polls.
+__device__ __forceinline__ uint4* ll_results(const RefineArgs& a, int grp) {
+    return reinterpret_cast<uint4*>(a.scratch) + (size_t)grp * a.group * 4 * kSlot;
+}
+__device__ __forceinline__ uint4* ll_mailboxes(const RefineArgs& a, int grp) { return ll_results(a, grp) + (size_t)a.group * 2 * kSlot; }
+
 // Phase clock of block 0 / thread 0: adds the cycles since the previous boundary to prof[i] (tools/refine_profile.py).
 __device__ __forceinline__ void tick(const RefineArgs& a, RefShared& sh, int i) {
     if (a.prof && blockIdx.x == 0 && threadIdx.x == 0) {
@@ -112,33 +133,35 @@ __device__ __forceinline__ void block_reduce_publish(double (&v)[NV], RefShared&
         __syncthreads();
         return;
     }
-    double* slots = a.scratch + (size_t)grp * (a.group + 2) * 2 * kSlot;
-    if (tid < NV) slots[((size_t)cta * 2 + (seq & 1)) * kSlot + tid] = s;
-    __syncthreads();  // the release below is cumulative over the slot writes of the other threads
-    if (tid == 0) st_release(&a.barrier[(size_t)grp * (a.group + 1) + cta], seq);
+    if (tid < NV) st_ll(ll_results(a, grp) + ((size_t)cta * 2 + (seq & 1)) * kSlot + tid, s, seq);
 }
 
 // Root: wait until every block of the group has published sequence number `seq`, then sum the slots in a fixed order.
 template <int NV>
 __device__ __forceinline__ void root_gather(RefShared& sh, const RefineArgs& a, int grp, unsigned seq) {
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const unsigned* flags = a.barrier + (size_t)grp * (a.group + 1);
-    const double* slots = a.scratch + (size_t)grp * (a.group + 2) * 2 * kSlot;
-    for (int c = tid; c < a.group; c += kRefThreads)
-        while (ld_acquire(&flags[c]) < seq) { }
-    __syncthreads();
-    tick(a, sh, 3);
-    // thread = (value v = lane, chunk of blocks = warp): up to 10 independent L2 loads in flight per thread (one round trip
-    // instead of a dependent chain), coalesced over v; partial sums per chunk, then the 16 chunks in a fixed order
+    const uint4* res = ll_results(a, grp);
+    // thread = (value v = lane, chunk of blocks = warp): up to 10 independent L2 loads in flight per thread, coalesced over v;
+    // an element that is not there yet is simply loaded again; partial sums per chunk, then the 16 chunks in a fixed order
     {
         double s = 0;
         if (lane < NV) {
             for (int base = 0; base < a.group; base += 10 * kRefWarps) {
                 double x[10];
+                unsigned missing = 0;
 #pragma unroll
                 for (int k = 0; k < 10; ++k) {
                     const int c = base + warp + k * kRefWarps;
-                    x[k] = c < a.group ? __ldcg(&slots[((size_t)c * 2 + (seq & 1)) * kSlot + lane]) : 0.;
+                    x[k] = 0.;
+                    if (c < a.group && !ld_ll(res + ((size_t)c * 2 + (seq & 1)) * kSlot + lane, seq, x[k])) missing |= 1u << k;
+                }
+                while (missing) {
+#pragma unroll
+                    for (int k = 0; k < 10; ++k)
+                        if (missing >> k & 1u) {
+                            const int c = base + warp + k * kRefWarps;
+                            if (ld_ll(res + ((size_t)c * 2 + (seq & 1)) * kSlot + lane, seq, x[k])) missing &= ~(1u << k);
+                        }
                 }
 #pragma unroll
                 for (int k = 0; k < 10; ++k) s += x[k];
@@ -146,6 +169,7 @@ __device__ __forceinline__ void root_gather(RefShared& sh, const RefineArgs& a, 
         }
         sh.red[warp][lane] = s;
     }
+    tick(a, sh, 3);
     __syncthreads();
     if (tid < NV) {
         double s = 0;
@@ -550,8 +574,6 @@ __global__ void __launch_bounds__(kRefThreads, 1) refine_kernel(const __grid_con
     const float* pl = nullptr;
     uint32_t* mbase = nullptr;
     double cen[3] = {0., 0., 0.};
-    unsigned* bflag = a.barrier + (size_t)grp * (a.group + 1) + a.group;                  // the root's command flag
-    double* bcast = a.scratch + ((size_t)grp * (a.group + 2) + a.group) * 2 * kSlot;      // two command records
     if (a.prof && blockIdx.x == 0 && tid == 0) sh.prof_last = clock64();
     if (root && tid == 0) { sh.job = -1; sh.finished = 1; }
     __syncthreads();
@@ -605,19 +627,22 @@ __global__ void __launch_bounds__(kRefThreads, 1) refine_kernel(const __grid_con
                 }
             }
             __syncwarp();
-            if (a.group > 1) {
-                const unsigned next = seq + 1u;
-                if (lane < C_COUNT) bcast[(size_t)(next & 1) * kSlot + lane] = sh.cmd[lane];
-                __syncwarp();
-                if (lane == 0) st_release(bflag, next);
-            }
         }
         ++seq;
-        // ================= everybody: receive the command =================
-        if (a.group > 1 && !root) {
-            if (tid == 0) while (ld_acquire(bflag) < seq) { }
-            __syncthreads();
-            if (tid < C_COUNT) sh.cmd[tid] = __ldcg(&bcast[(size_t)(seq & 1) * kSlot + tid]);
+        if (a.group > 1) {
+            if (root) {  // every block gets its own copy of the command (all threads of the root write)
+                __syncthreads();
+                uint4* mb = ll_mailboxes(a, grp);
+                for (int i = tid; i < (a.group - 1) * C_COUNT; i += kRefThreads) {
+                    const int c = 1 + i / C_COUNT, e = i - (c - 1) * C_COUNT;
+                    st_ll(mb + ((size_t)c * 2 + (seq & 1)) * kSlot + e, sh.cmd[e], seq);
+                }
+            } else if (tid < C_COUNT) {
+                const uint4* mine = ll_mailboxes(a, grp) + ((size_t)cta * 2 + (seq & 1)) * kSlot + tid;
+                double v;
+                while (!ld_ll(mine, seq, v)) { }
+                sh.cmd[tid] = v;
+            }
         }
         __syncthreads();
         tick(a, sh, 0);
@@ -754,8 +779,8 @@ void launch_refine(const RefineArgs& a, int n_groups, cudaStream_t st) {
 int refine_cache_words() { return kCacheWords; }
 size_t refine_cache_bytes() { return (size_t)3 * kCacheCells * sizeof(float) + (size_t)kCacheCells * sizeof(unsigned short); }
 int refine_max_compact_words() { return kMaxCompactWords; }
-// scratch doubles / flag words a launch of n_groups x group blocks needs
-size_t refine_scratch_doubles(int n_groups, int group) { return (size_t)n_groups * (group + 2) * 2 * kSlot; }
+// scratch doubles (zeroed before every launch: LL elements) / flag words a launch of n_groups x group blocks needs
+size_t refine_scratch_doubles(int n_groups, int group) { return (size_t)n_groups * group * 4 * kSlot * 2; }
 size_t refine_flag_words(int n_groups, int group) { return (size_t)n_groups * (group + 1); }
 
 int refine_max_coresident_blocks(int sm_count) {
