@@ -366,58 +366,72 @@ ESAC_HD T quad3(const T D[9], const T a[3], const T b[3]) {  // a^T D b
            a[2] * (D[6] * b[0] + D[7] * b[1] + D[8] * b[2]);
 }
 
+// Real roots of c3 g^3 + c2 g^2 + c1 g + c0, produced ON DEMAND: the P3P below almost always needs only the first one, and a
+// root costs a cosine plus a Newton polish with four divisions -- a third of the solver's dependency chain when all three are
+// computed up front.  cubic_setup returns the number of real roots, cubic_root(i) the i-th of them.
 template <typename T>
-ESAC_HD int real_cubic_roots(T c3, T c2, T c1, T c0, T roots[3]) {
+struct Cubic {
+    T a, b, c;       // monic coefficients
+    T sq, th;        // three real roots: -2 sqrt(Q), acos(R / sqrt(Q^3))
+    T r0, r1;        // closed-form roots of the degenerate (quadratic / linear) and the one-real-root case
+    int kind;        // 0: r0 / r1 as they are, 1: trigonometric
+};
+template <typename T>
+ESAC_HD int cubic_setup(T c3, T c2, T c1, T c0, Cubic<T>& q) {
     using N = Num<T>;
-    int n = 0;
+    q.kind = 0; q.r0 = q.r1 = 0; q.a = q.b = q.c = 0; q.sq = q.th = 0;
     T scale = N::abs_(c3) + N::abs_(c2) + N::abs_(c1) + N::abs_(c0);
     if (!(scale > 0)) return 0;
     if (N::abs_(c3) < N::kRelTiny * scale) {  // quadratic (the root at infinity is handled by the caller)
         if (N::abs_(c2) < N::kRelTiny * scale) {
-            if (N::abs_(c1) > 0) roots[n++] = N::div_(-c0, c1);
-            return n;
+            if (N::abs_(c1) > 0) { q.r0 = N::div_(-c0, c1); return 1; }
+            return 0;
         }
         T disc = c1 * c1 - 4 * c2 * c0;
         if (disc < 0) return 0;
         T sq = N::sqrt_(disc);
-        T q = T(-0.5) * (c1 + (c1 >= 0 ? sq : -sq));
-        roots[n++] = N::div_(q, c2);
-        if (q != 0) roots[n++] = N::div_(c0, q);
-        return n;
+        T w = T(-0.5) * (c1 + (c1 >= 0 ? sq : -sq));
+        q.r0 = N::div_(w, c2);
+        if (w != 0) { q.r1 = N::div_(c0, w); return 2; }
+        return 1;
     }
     const T ic3 = N::div_(T(1), c3);
-    T a = c2 * ic3, b = c1 * ic3, c = c0 * ic3;
+    q.a = c2 * ic3; q.b = c1 * ic3; q.c = c0 * ic3;
+    const T a = q.a, b = q.b, c = q.c;
     T Q = (a * a - 3 * b) * T(1.0 / 9.0), Rr = (2 * a * a * a - 9 * a * b + 27 * c) * T(1.0 / 54.0);
     T Q3 = Q * Q * Q;
     if (Rr * Rr < Q3) {
-        T th = N::acos_(N::div_(Rr, N::sqrt_(Q3)));
-        T sq = -2 * N::sqrt_(Q);
-        const T twopi = T(2 * 3.14159265358979323846);
-        const T third = T(1.0 / 3.0);
-        roots[0] = sq * N::cos_(th * third) - a * third;
-        roots[1] = sq * N::cos_((th + twopi) * third) - a * third;
-        roots[2] = sq * N::cos_((th - twopi) * third) - a * third;
-        n = 3;
-    } else {
-        T A = -(Rr >= 0 ? T(1) : T(-1)) * N::cbrt_(N::abs_(Rr) + N::sqrt_(Rr * Rr - Q3));
-        T B = A != 0 ? N::div_(Q, A) : 0;
-        roots[0] = A + B - a * T(1.0 / 3.0);
-        n = 1;
+        q.th = N::acos_(N::div_(Rr, N::sqrt_(Q3)));
+        q.sq = -2 * N::sqrt_(Q);
+        q.kind = 1;
+        return 3;
     }
-#pragma unroll 1
-    for (int i = 0; i < n; ++i) {  // Newton polish on the monic cubic
-        T g = roots[i];
-        for (int it = 0; it < 4; ++it) {
-            T fv = ((g + a) * g + b) * g + c;
-            T dv = (3 * g + 2 * a) * g + b;
-            if (!(N::abs_(dv) > 0)) break;
-            g -= N::div_(fv, dv);
-        }
-        roots[i] = g;
-    }
-    return n;
+    T A = -(Rr >= 0 ? T(1) : T(-1)) * N::cbrt_(N::abs_(Rr) + N::sqrt_(Rr * Rr - Q3));
+    T B = A != 0 ? N::div_(Q, A) : 0;
+    q.r0 = A + B - a * T(1.0 / 3.0);
+    q.kind = 2;
+    return 1;
 }
-
+template <typename T>
+ESAC_HD T cubic_root(const Cubic<T>& q, int i) {
+    using N = Num<T>;
+    if (q.kind == 0) return i == 0 ? q.r0 : q.r1;
+    T g;
+    if (q.kind == 1) {
+        const T twopi = T(2 * 3.14159265358979323846), third = T(1.0 / 3.0);
+        const T ang = i == 0 ? q.th : (i == 1 ? q.th + twopi : q.th - twopi);
+        g = q.sq * N::cos_(ang * third) - q.a * third;
+    } else {
+        g = q.r0;
+    }
+    for (int it = 0; it < 4; ++it) {  // Newton polish on the monic cubic
+        T fv = ((g + q.a) * g + q.b) * g + q.c;
+        T dv = (3 * g + 2 * q.a) * g + q.b;
+        if (!(N::abs_(dv) > 0)) break;
+        g -= N::div_(fv, dv);
+    }
+    return g;
+}
 // Intersect the line {lam : l.lam = 0} with the conic lam^T D lam = 0; appends direction vectors.
 // (kept out of line: three call sites, and the sampling prefilter is instruction-cache bound)
 template <typename T>
@@ -492,11 +506,12 @@ ESAC_HD bool tri_frame(const T p0[3], const T p1[3], const T p2[3], T F[9]) {
     return true;
 }
 
-// Rigid transform mapping triangle x (scene) onto triangle P (camera): R row-major, t.
+// Rigid transform mapping triangle x (scene; its frame Fw = tri_frame(x) is the same for every candidate, so the caller
+// computes it once) onto triangle P (camera): R row-major, t.
 template <typename T>
-ESAC_HD bool align_triangles(const T P[3][3], const T x[3][3], T R[9], T t[3]) {
-    T Fc[9], Fw[9];
-    if (!tri_frame(P[0], P[1], P[2], Fc) || !tri_frame(x[0], x[1], x[2], Fw)) return false;
+ESAC_HD bool align_triangles(const T P[3][3], const T x[3][3], const T Fw[9], T R[9], T t[3]) {
+    T Fc[9];
+    if (!tri_frame(P[0], P[1], P[2], Fc)) return false;
     for (int r = 0; r < 3; ++r)
         for (int c = 0; c < 3; ++c)
             R[r * 3 + c] = Fc[r * 3 + 0] * Fw[c * 3 + 0] + Fc[r * 3 + 1] * Fw[c * 3 + 1] + Fc[r * 3 + 2] * Fw[c * 3 + 2];
@@ -546,8 +561,8 @@ ESAC_HD int p3p_lambdas(const T y[3][3], const T x[3][3], T lam[4][3], T& amax, 
     adj3(D1, B1);
     adj3(D2, B2);
     T k0 = det3(D1), k1 = trace_prod3(B1, D2), k2 = trace_prod3(D1, B2), k3 = det3(D2);
-    T roots[4];
-    int nr = real_cubic_roots(k3, k2, k1, k0, roots);
+    Cubic<T> cub;
+    const int nr = cubic_setup(k3, k2, k1, k0, cub);
     T kscale = N::abs_(k3) + N::abs_(k2) + N::abs_(k1) + N::abs_(k0);
     bool inf_root = N::abs_(k3) < N::kRelTiny * kscale;
     T dirs[8][3];
@@ -560,7 +575,7 @@ ESAC_HD int p3p_lambdas(const T y[3][3], const T x[3][3], T lam[4][3], T& amax, 
             for (int i = 0; i < 9; ++i) D0[i] = D2[i];
             Dother = D1;
         } else {
-            T g = roots[ri];
+            T g = cubic_root(cub, ri);
             if (N::abs_(g) <= 1) {
                 for (int i = 0; i < 9; ++i) D0[i] = D1[i] + g * D2[i];
                 Dother = D2;
@@ -643,6 +658,8 @@ ESAC_HDN int p3p_solve(const double y[3][3], const double x[3][3], double Rs[4][
     bool unc;
     int nl = p3p_lambdas<double>(y, x, lams, amax, cs, ss, unc);
     const double c12 = cs[0], c13 = cs[1], c23 = cs[2], s12 = ss[0], s13 = ss[1], s23 = ss[2];
+    double Fw[9];
+    if (nl > 0 && !tri_frame<double>(x[0], x[1], x[2], Fw)) return 0;
     int ns = 0;
     for (int d = 0; d < nl && ns < 4; ++d) {
         double lam[3] = {lams[d][0], lams[d][1], lams[d][2]};
@@ -666,7 +683,7 @@ ESAC_HDN int p3p_solve(const double y[3][3], const double x[3][3], double Rs[4][
         double P[3][3];
         for (int i = 0; i < 3; ++i)
             for (int c = 0; c < 3; ++c) P[i][c] = lam[i] * sa * y[i][c];
-        if (!align_triangles<double>(P, x, Rs[ns], ts[ns])) continue;
+        if (!align_triangles<double>(P, x, Fw, Rs[ns], ts[ns])) continue;
         bool dup = false;  // reject duplicates (double roots)
         for (int q = 0; q < ns; ++q) {
             double dd = 0;

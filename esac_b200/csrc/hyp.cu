@@ -319,7 +319,8 @@ __global__ void __launch_bounds__(64) emit_kernel(const __grid_constant__ Sample
 // ev_half[0]; lane 1 = the rest, released by ev_half[1], so lane 0 samples while the second half is on the wire.
 // What was tried on top of this and measured slower or equal (profiles/r02h_*.txt): 3-4 lanes, one
 // prefilter stream + per-lane verdict streams in forced anti-phase, other window policies, a single persistent kernel with
-// work / survivor queues.  option sample_trace shows who runs when.
+// work / survivor queues, programmatic dependent launch between the kernels of a lane (the ~4 us gaps close, but the early
+// CTAs of one lane starve the other).  option sample_trace shows who runs when.
 int launch_sample(const float* coords, float4* coords4, const int* assign32, const Problem& P, uint64_t seed, int max_tries,
                   const int* injected, int inj_T, const SampleState* st, int n_lanes, int sm_count, int use_prefilter,
                   int hyp_offset, int hyp_stride, Pose* poses, int* cells, int* tries, const cudaStream_t* lanes,

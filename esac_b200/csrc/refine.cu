@@ -156,6 +156,7 @@ __device__ __forceinline__ void root_gather(RefShared& sh, const RefineArgs& a, 
                     if (c < a.group && !ld_ll(res + ((size_t)c * 2 + (seq & 1)) * kSlot + lane, seq, x[k])) missing |= 1u << k;
                 }
                 while (missing) {
+                    __nanosleep(32);  // do not hammer lines their writers are about to store to
 #pragma unroll
                     for (int k = 0; k < 10; ++k)
                         if (missing >> k & 1u) {
@@ -640,7 +641,7 @@ __global__ void __launch_bounds__(kRefThreads, 1) refine_kernel(const __grid_con
             } else if (tid < C_COUNT) {
                 const uint4* mine = ll_mailboxes(a, grp) + ((size_t)cta * 2 + (seq & 1)) * kSlot + tid;
                 double v;
-                while (!ld_ll(mine, seq, v)) { }
+                while (!ld_ll(mine, seq, v)) __nanosleep(32);  // (polling flat out slows the root's stores to these very lines)
                 sh.cmd[tid] = v;
             }
         }
