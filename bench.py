@@ -281,7 +281,7 @@ def run_configs(rank: int, world: int, dev, api, sharded, dist, reps: int = 4):
         "stages_ms_by_rank_forward": st_f, "stages_ms_by_rank_backward": st_b,
         "parallelism": "single GPU" if world == 1 else "hypothesis-major shard (all planes on every rank, hypotheses dealt round-robin); forward: "
                        "1 ncclAllGather; backward: ncclAllGather of (max, sum exp) + ncclAllReduce of the expectation + "
-                       "ncclAllReduce of the 74 MB gradient tensor",
+                       "ncclAllReduce of the gradient planes that received contributions on some rank (3.7 of 74 MB here)",
         "note": "the gating puts 60% of the hypotheses and every contributing one on the true expert: dealing experts to ranks "
                 "would leave the refine-all stage on one GPU, dealing hypotheses spreads it"}
     return out

@@ -456,6 +456,20 @@ __global__ void add_inplace_scalar_kernel(float* __restrict__ dst, const float* 
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) dst[i] += src[i];
 }
 
+// flags[e] = 1 when expert e has a contributing hypothesis (p >= PROB_THRESH) on this rank: only those planes receive gradient
+__global__ void expert_flags_kernel(const int* contrib, const int* n_contrib, const int* assign32, int E, int* flags) {
+    for (int e = threadIdx.x; e < E; e += blockDim.x) flags[e] = 0;
+    __syncthreads();
+    const int n = *n_contrib;
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+        const int e = assign32[contrib[i]];
+        if (e >= 0 && e < E) flags[e] = 1;
+    }
+}
+void launch_expert_flags(const int* contrib, const int* n_contrib, const int* assign32, int E, int* flags, cudaStream_t st) {
+    expert_flags_kernel<<<1, 256, 0, st>>>(contrib, n_contrib, assign32, E, flags);
+}
+
 void launch_add_inplace(float* dst, const float* src, size_t n, cudaStream_t st) {
     if ((((uintptr_t)dst) | ((uintptr_t)src)) & 15) add_inplace_scalar_kernel<<<1184, 256, 0, st>>>(dst, src, n);  // unaligned views
     else add_inplace_kernel<<<1184, 256, 0, st>>>(dst, src, n);

@@ -71,6 +71,8 @@ struct esacb200_ctx {
     int max_ref_steps = 100;
     int fixed_seed = 0;
     int refine_group_opt = 0;
+    int* h_flags = nullptr;    // pinned: per-expert "receives gradient on some rank" flags (hypothesis-major sharding)
+    int h_flags_cap = 0;
     int refine_compact = 1;    // LM evaluations over per-CTA inlier lists instead of predicated passes over all cells
     int refine_profile = 0;    // 1: block 0 of the refinement kernel records phase cycle counts (esacb200_get_refine_profile)
     int refine_jobs_per_group = 3;
@@ -89,7 +91,7 @@ struct esacb200_ctx {
     // workspace
     DevBuf coords, grads, assign64, assign32, counts, offsets, perm, slot_of, chunks, scalars, centres, poses, poses_ref,
         cells, tries, posepk, part, scores, probs, stats, contrib, masks, rounds, scratch, barrier, out17, inject,
-        losses, red, hypgrad, job_of, gt, smp_int, smp_surv, smp_trace, clist, coords4, coords_alt, assign64_alt, out_batch, prof;
+        losses, red, hypgrad, job_of, gt, smp_int, smp_surv, smp_trace, clist, eflags, coords4, coords_alt, assign64_alt, out_batch, prof;
     float* h_out = nullptr;  // pinned staging: 32 floats
     double* h_dbl = nullptr; // pinned staging: 8 doubles
     int inj_M = 0, inj_T = 0;
@@ -140,6 +142,8 @@ struct NcclApi {
 constexpr int kNcclFloat32 = 7;  // ncclFloat
 constexpr int kNcclFloat64 = 8;  // ncclDouble
 constexpr int kNcclSum = 0;      // ncclSum
+constexpr int kNcclInt32 = 2;    // ncclInt32
+constexpr int kNcclMax = 2;      // ncclMax
 
 NcclApi& nccl_api() {
     static NcclApi api;
@@ -614,11 +618,12 @@ void esacb200_destroy(esacb200_ctx* ctx) {
                       &ctx->slot_of, &ctx->chunks, &ctx->scalars, &ctx->centres, &ctx->poses, &ctx->poses_ref, &ctx->cells,
                       &ctx->tries, &ctx->posepk, &ctx->part, &ctx->scores, &ctx->probs, &ctx->stats, &ctx->contrib,
                       &ctx->masks, &ctx->rounds, &ctx->scratch, &ctx->barrier, &ctx->out17, &ctx->inject, &ctx->losses,
-                      &ctx->red, &ctx->hypgrad, &ctx->job_of, &ctx->gt, &ctx->smp_int, &ctx->smp_surv, &ctx->smp_trace, &ctx->clist, &ctx->coords4, &ctx->coords_alt, &ctx->assign64_alt, &ctx->out_batch, &ctx->prof, &ctx->gathered, &ctx->grads_work};
+                      &ctx->red, &ctx->hypgrad, &ctx->job_of, &ctx->gt, &ctx->smp_int, &ctx->smp_surv, &ctx->smp_trace, &ctx->clist, &ctx->eflags, &ctx->coords4, &ctx->coords_alt, &ctx->assign64_alt, &ctx->out_batch, &ctx->prof, &ctx->gathered, &ctx->grads_work};
     for (DevBuf* b : bufs) b->release();
     for (int i = 0; i < EV_COUNT; ++i)
         if (ctx->ev[i]) cudaEventDestroy(ctx->ev[i]);
     if (ctx->h_out) cudaFreeHost(ctx->h_out);
+    if (ctx->h_flags) cudaFreeHost(ctx->h_flags);
     if (ctx->h_dbl) cudaFreeHost(ctx->h_dbl);
     for (int i = 0; i < 2; ++i) {
         if (ctx->ev_copied[i]) cudaEventDestroy(ctx->ev_copied[i]);
@@ -1013,6 +1018,36 @@ int esacb200_refine_poses(esacb200_ctx* ctx, const float* coords, int E, int H, 
 } ESAC_ABI_CATCH(ctx)
 
 
+// Hypothesis-major sharding: the planes that receive gradient on SOME rank (flags after the max-all-reduce, host copy in
+// ctx->h_flags) are the only ones whose slices have to be summed over the ranks -- with a peaked gating that is one plane of
+// twenty (3.7 of 74 MB at 480x640).  phase 0: zero those slices of the work buffer; phase 1: all-reduce them and add them to dst.
+static int ensure_host_flags(esacb200_ctx* ctx, int E) {
+    if (ctx->h_flags_cap >= E + 1) return 0;
+    if (ctx->h_flags) cudaFreeHost(ctx->h_flags);
+    ctx->h_flags = nullptr; ctx->h_flags_cap = 0;
+    CK(cudaMallocHost((void**)&ctx->h_flags, (size_t)(E + 1) * sizeof(int)));
+    ctx->h_flags_cap = E + 1;
+    return 0;
+}
+static int for_flagged_planes(esacb200_ctx* ctx, int E, size_t plane, float* work, float* dst, int phase) {
+    for (int e = 0; e < E;) {
+        if (!ctx->h_flags[e]) { ++e; continue; }
+        int e1 = e;
+        while (e1 < E && ctx->h_flags[e1]) ++e1;
+        float* w = work + (size_t)e * plane;
+        const size_t n = (size_t)(e1 - e) * plane;
+        if (phase == 0) {
+            CK(cudaMemsetAsync(w, 0, n * sizeof(float), ctx->stream));
+        } else {
+            CKN(nccl_api().AllReduce(w, w, n, kNcclFloat32, kNcclSum, ctx->nccl_comm, ctx->stream));
+            launch_add_inplace(dst + (size_t)e * plane, w, n, ctx->stream);
+            ctx->st.kernel_launches += 2;
+        }
+        e = e1;
+    }
+    return 0;
+}
+
 // -------------------------------------------------------------------------------------------------
 static int backward_impl(esacb200_ctx* ctx, const float* coords, float* grads, int E, int H, int W, const int64_t* assign,
                          int64_t assign_stride, int M, const float* gt_pose, float wRot, float wTrans, float cut, int shiftX,
@@ -1042,8 +1077,9 @@ static int backward_impl(esacb200_ctx* ctx, const float* coords, float* grads, i
     float* d_dst = d_grads;
     if (reduce_grads) {
         CK(ctx->grads_work.ensure(cbytes));
-        CK(cudaMemsetAsync(ctx->grads_work.p, 0, cbytes, ctx->stream));
-        d_grads = ctx->grads_work.as<float>();
+        d_grads = ctx->grads_work.as<float>();  // (the slices that will be used are zeroed once they are known, below)
+        rc = ensure_host_flags(ctx, E);
+        if (rc) return rc;
     }
     rc = stage_inputs(ctx, pl, coords, assign, assign_stride);
     if (rc) return rc;
@@ -1076,7 +1112,18 @@ static int backward_impl(esacb200_ctx* ctx, const float* coords, float* grads, i
     // barrier longer than needed: one 4-byte read-back of the number of contributing hypotheses (a ~20 us stall on a
     // multi-millisecond call) lets the group size be coresident / jobs.
     CK(cudaMemcpyAsync(ctx->h_out + 28, sc + S_NCONTRIB, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    if (reduce_grads) {  // which planes receive gradient on some rank: rides on the same host synchronisation
+        CK(ctx->eflags.ensure((size_t)E * sizeof(int)));
+        launch_expert_flags(ctx->contrib.as<int>(), sc + S_NCONTRIB, ctx->assign32.as<int>(), E, ctx->eflags.as<int>(), ctx->stream);
+        CKN(nccl_api().AllReduce(ctx->eflags.p, ctx->eflags.p, (size_t)E, kNcclInt32, kNcclMax, ctx->nccl_comm, ctx->stream));
+        CK(cudaMemcpyAsync(ctx->h_flags, ctx->eflags.p, (size_t)E * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+        ctx->st.kernel_launches += 2;
+    }
     CK(cudaStreamSynchronize(ctx->stream));
+    if (reduce_grads) {
+        rc = for_flagged_planes(ctx, E, (size_t)3 * P.N, d_grads, d_dst, 0);
+        if (rc) return rc;
+    }
     int n_jobs_now = *(const int*)(ctx->h_out + 28);
     if (n_jobs_now < 1) n_jobs_now = 1;
     int group = pick_group(ctx, P, n_jobs_now);
@@ -1144,10 +1191,9 @@ static int backward_impl(esacb200_ctx* ctx, const float* coords, float* grads, i
     CK(cudaGetLastError());
     ctx->st.kernel_launches += 5;
     if (reduce_grads) {
-        CKN(nccl_api().AllReduce(d_grads, d_grads, (size_t)P.E * 3 * P.N, kNcclFloat32, kNcclSum, ctx->nccl_comm, ctx->stream));
-        launch_add_inplace(d_dst, d_grads, (size_t)P.E * 3 * P.N, ctx->stream);
+        rc = for_flagged_planes(ctx, E, (size_t)3 * P.N, d_grads, d_dst, 1);
+        if (rc) return rc;
         CK(cudaGetLastError());
-        ctx->st.kernel_launches += 2;
         d_grads = d_dst;
     }
     mark(ctx, EV_BWD);
@@ -1209,23 +1255,34 @@ int esacb200_backward_sharded_nccl(esacb200_ctx* ctx, const float* coords, float
     CK(ctx->gathered.ensure((size_t)ctx->comm_world * 2 * 8));
     ctx->h_dbl[0] = 0.; ctx->h_dbl[1] = -1e300; ctx->h_dbl[2] = 0.;  // stats[4] partial expectation, [5] max score, [6] sum exp
     CK(cudaMemcpyAsync(ctx->stats.as<double>() + 4, ctx->h_dbl, 3 * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+    // the collectives below come in the order backward_impl issues them on the ranks that do hold hypotheses
     CKN(nccl_api().AllGather(ctx->stats.as<double>() + 5, ctx->gathered.p, 2, kNcclFloat64, ctx->nccl_comm, ctx->stream));
-    CKN(nccl_api().AllReduce(ctx->stats.as<double>() + 4, ctx->stats.as<double>() + 7, 1, kNcclFloat64, kNcclSum, ctx->nccl_comm,
-                             ctx->stream));
+    const size_t n = reduce_grads ? (size_t)E * 3 * H * W : 0;
+    float* d_dst = grads;
     if (reduce_grads) {  // zero contribution to the gradient sum, then the sum is added to this rank's tensor like everywhere
         if (!grads || E <= 0 || H <= 0 || W <= 0) return fail(ctx, ESACB200_ERR_ARG, "reduce_grads needs the gradient tensor and its shape on every rank");
-        const size_t n = (size_t)E * 3 * H * W;
         CK(ctx->grads_work.ensure(n * 4));
-        CK(cudaMemsetAsync(ctx->grads_work.p, 0, n * 4, ctx->stream));
-        CKN(nccl_api().AllReduce(ctx->grads_work.p, ctx->grads_work.p, n, kNcclFloat32, kNcclSum, ctx->nccl_comm, ctx->stream));
-        if (is_device_ptr(grads)) {
-            launch_add_inplace(grads, ctx->grads_work.as<float>(), n, ctx->stream);
-        } else {
+        int rc = ensure_host_flags(ctx, E);
+        if (rc) return rc;
+        CK(ctx->eflags.ensure((size_t)E * sizeof(int)));
+        CK(cudaMemsetAsync(ctx->eflags.p, 0, (size_t)E * sizeof(int), ctx->stream));
+        CKN(nccl_api().AllReduce(ctx->eflags.p, ctx->eflags.p, (size_t)E, kNcclInt32, kNcclMax, ctx->nccl_comm, ctx->stream));
+        CK(cudaMemcpyAsync(ctx->h_flags, ctx->eflags.p, (size_t)E * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+        CK(cudaStreamSynchronize(ctx->stream));
+        if (!is_device_ptr(grads)) {
             CK(ctx->grads.ensure(n * 4));
             CK(cudaMemcpyAsync(ctx->grads.p, grads, n * 4, cudaMemcpyHostToDevice, ctx->stream));
-            launch_add_inplace(ctx->grads.as<float>(), ctx->grads_work.as<float>(), n, ctx->stream);
-            CK(cudaMemcpyAsync(grads, ctx->grads.p, n * 4, cudaMemcpyDeviceToHost, ctx->stream));
+            d_dst = ctx->grads.as<float>();
         }
+        rc = for_flagged_planes(ctx, E, (size_t)3 * H * W, ctx->grads_work.as<float>(), d_dst, 0);
+        if (rc) return rc;
+    }
+    CKN(nccl_api().AllReduce(ctx->stats.as<double>() + 4, ctx->stats.as<double>() + 7, 1, kNcclFloat64, kNcclSum, ctx->nccl_comm,
+                             ctx->stream));
+    if (reduce_grads) {
+        int rc = for_flagged_planes(ctx, E, (size_t)3 * H * W, ctx->grads_work.as<float>(), d_dst, 1);
+        if (rc) return rc;
+        if (!is_device_ptr(grads)) CK(cudaMemcpyAsync(grads, ctx->grads.p, n * 4, cudaMemcpyDeviceToHost, ctx->stream));
         CK(cudaGetLastError());
     }
     CK(cudaMemcpyAsync(ctx->h_dbl + 4, ctx->stats.as<double>() + 7, sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));

@@ -205,6 +205,7 @@ void launch_backward(const BwdArgs& a, int max_jobs, cudaStream_t st);
 // phase split for the multi-GPU path: losses + local expectation only / everything after the loss exchange
 void launch_backward_losses(const BwdArgs& a, cudaStream_t st);
 void launch_add_inplace(float* dst, const float* src, size_t n, cudaStream_t st);
+void launch_expert_flags(const int* contrib, const int* n_contrib, const int* assign32, int E, int* flags, cudaStream_t st);
 size_t bwd_hypgrad_bytes();
 int bwd_red_vals();
 int bwd_tiles(int N);
