@@ -286,14 +286,29 @@ __device__ __forceinline__ void lm_accumulate_list(const float* __restrict__ pl,
 #pragma unroll
     for (int i = 0; i < kRedN + 1; ++i) acc[i] = 0;
     const double f = (double)P.f, cx = (double)P.ppx, cy = (double)P.ppy;
-    for (int i = threadIdx.x; i < n; i += kRefThreads) {
-        const int lc = list[i];
+    // software pipeline: the list entry and the three coordinates of the NEXT cell are requested before the ~95 fp64
+    // instructions of the current one (uncached shares read both from L2: two dependent round trips per cell otherwise,
+    // which 4 warps per scheduler do not cover)
+    int i = threadIdx.x;
+    int lc_n = 0;
+    float Xn = 0.f, Yn = 0.f, Zn = 0.f;
+    if (i < n) {
+        lc_n = list[i];
+        if (CACHED) { Xn = cache[lc_n]; Yn = cache[kCacheCells + lc_n]; Zn = cache[2 * kCacheCells + lc_n]; }
+        else { const int p = w0 * 32 + lc_n; Xn = pl[p]; Yn = pl[P.N + p]; Zn = pl[2 * (size_t)P.N + p]; }
+    }
+    for (; i < n; i += kRefThreads) {
+        const int lc = lc_n;
+        const float Xf = Xn, Yf = Yn, Zf = Zn;
+        const int i2 = i + kRefThreads;
+        if (i2 < n) {
+            lc_n = list[i2];
+            if (CACHED) { Xn = cache[lc_n]; Yn = cache[kCacheCells + lc_n]; Zn = cache[2 * kCacheCells + lc_n]; }
+            else { const int p2 = w0 * 32 + lc_n; Xn = pl[p2]; Yn = pl[P.N + p2]; Zn = pl[2 * (size_t)P.N + p2]; }
+        }
         const int p = w0 * 32 + lc;
         const int yy = p / P.W, xx = p - yy * P.W;
         const double px = (double)(xx * P.sub + P.sub / 2 - P.shiftX), py = (double)(yy * P.sub + P.sub / 2 - P.shiftY);
-        float Xf, Yf, Zf;
-        if (CACHED) { Xf = cache[lc]; Yf = cache[kCacheCells + lc]; Zf = cache[2 * kCacheCells + lc]; }
-        else { Xf = pl[p]; Yf = pl[P.N + p]; Zf = pl[2 * (size_t)P.N + p]; }
         const double X = (double)Xf - c[0], Y = (double)Yf - c[1], Z = (double)Zf - c[2];
         const double qx = R[0] * X + R[1] * Y + R[2] * Z;
         const double qy = R[3] * X + R[4] * Y + R[5] * Z;
