@@ -73,6 +73,7 @@ struct esacb200_ctx {
     int refine_group_opt = 0;
     int* h_flags = nullptr;    // pinned: per-expert "receives gradient on some rank" flags (hypothesis-major sharding)
     int h_flags_cap = 0;
+    int refine_pretest = 1;    // inlier selection: float pretest with a rounding-error bound, exact arithmetic only where in doubt
     int refine_compact = 1;    // LM evaluations over per-CTA inlier lists instead of predicated passes over all cells
     int refine_profile = 0;    // 1: block 0 of the refinement kernel records phase cycle counts (esacb200_get_refine_profile)
     int refine_jobs_per_group = 3;
@@ -482,6 +483,7 @@ int run_refine(esacb200_ctx* ctx, const Plan& pl, const Pose* in, Pose* out, con
     const int wpc = (words + group - 1) / group;
     a.cache = wpc <= refine_cache_words() ? 1 : 0;
     a.compact = ctx->refine_compact;
+    a.pretest = ctx->refine_pretest;
     a.clist = nullptr;
     if (a.compact && !a.cache && wpc <= refine_max_compact_words()) {
         CK(ctx->clist.ensure((size_t)n_groups * words * 32 * sizeof(unsigned short)));
@@ -662,6 +664,7 @@ int esacb200_set_option(esacb200_ctx* ctx, const char* key, double v) {
     else if (!strcmp(key, "max_ref_steps")) ctx->max_ref_steps = v < 0 ? 0 : (int)v;
     else if (!strcmp(key, "fixed_seed")) ctx->fixed_seed = v != 0;
     else if (!strcmp(key, "refine_group")) ctx->refine_group_opt = (int)v;
+    else if (!strcmp(key, "refine_pretest")) ctx->refine_pretest = v != 0;
     else if (!strcmp(key, "refine_compact")) ctx->refine_compact = v != 0;
     else if (!strcmp(key, "refine_profile")) ctx->refine_profile = v != 0;
     else if (!strcmp(key, "refine_jobs_per_group")) ctx->refine_jobs_per_group = v < 1 ? 1 : (int)v;
@@ -1340,6 +1343,7 @@ int esacb200_backward_batch(esacb200_ctx* ctx, int B, const float* coords, float
         w->refine_group_opt = ctx->refine_group_opt;
         w->refine_jobs_per_group = ctx->refine_jobs_per_group;
         w->refine_compact = ctx->refine_compact;
+        w->refine_pretest = ctx->refine_pretest;
         w->sample_prefilter = ctx->sample_prefilter;
         w->sample_tail_boost = ctx->sample_tail_boost;
         w->hyp_offset = ctx->hyp_offset;

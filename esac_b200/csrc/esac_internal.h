@@ -140,6 +140,7 @@ struct RefineArgs {
     int group;               // CTAs cooperating on one job
     int cache;               // 1: every CTA's share of the map fits the shared-memory cell cache
     int compact;             // 1: LM evaluations walk a per-CTA list of the round's inlier cells
+    int pretest;             // 1: the inlier selection classifies clear cases in fp32 (error-bounded), exact arithmetic for the rest
     unsigned short* clist;   // [n_groups][words * 32] inlier lists of blocks whose share does not fit shared memory (or null)
     long long* prof;         // diagnostics: 16 cycle counters of block 0 (null = off)
     Problem P;

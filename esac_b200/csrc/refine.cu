@@ -182,6 +182,14 @@ __device__ __forceinline__ void root_gather(RefShared& sh, const RefineArgs& a, 
     tick(a, sh, 4);
 }
 
+// (row, column) of cell p without an integer division: magic = ceil(2^32 / W) gives floor(p / W) or one more
+__device__ __forceinline__ void cell_xy(int p, int W, unsigned magic, int& yy, int& xx) {
+    int q = (int)__umulhi((unsigned)p, magic);
+    int r = p - q * W;
+    if (r < 0) { --q; r += W; }
+    yy = q; xx = r;
+}
+
 // Per-cell contribution to J^T J (21, upper triangle, row-major) and J^T r (6) for the two residual rows
 //   Ju = (c qy, a qz - c qx, -a qy, a, 0, c),  Jv = (-a qz + d qy, -d qx, a qx, 0, a, d)
 // written out so the structural zeros cost nothing (x * 0 cannot be dropped by the compiler under IEEE rules).
@@ -278,6 +286,67 @@ __device__ __forceinline__ void lm_accumulate(const float* __restrict__ pl, cons
     }
 }
 
+// Selection pass of a round: the inlier bit of every cell of the share at the round's pose.  What decides is getReproErrs'
+// arithmetic (repro_err_f: fp64 transform, float-rounded projection, float difference, `< tau`), but it only has to be
+// carried out where the answer is in doubt: a float evaluation of the same error (coordinates relative to the plane centre,
+// like the scoring kernel) comes with a running bound on its own rounding error, and a cell whose error is further from tau
+// than that bound plus 4e-3 px is classified by it -- ~35 fp32 instructions instead of ~60 fp64 ones (each of which occupies
+// the fp64 pipe 2.7 times as long) for all but a fraction of a percent of the cells.  NaNs fail both comparisons and take the
+// exact path.  tc = R c + t0 (the command's t), t0 the true translation.
+template <bool CACHED>
+__device__ __forceinline__ void lm_select(const float* __restrict__ pl, const float* __restrict__ cache, const Problem& P,
+                                          const double* R, const double* t0, const double* tc, const double* c, uint32_t* mask,
+                                          int w0, int w1, int* cnt, bool use_pretest) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const double f = (double)P.f, cx = (double)P.ppx, cy = (double)P.ppy;
+    const float A0 = (float)R[0], A1 = (float)R[1], A2 = (float)R[2], A3 = (float)R[3], A4 = (float)R[4], A5 = (float)R[5];
+    const float A6 = (float)R[6], A7 = (float)R[7], A8 = (float)R[8];
+    const float b0 = (float)tc[0], b1 = (float)tc[1], b2 = (float)tc[2];
+    const float c0 = (float)c[0], c1 = (float)c[1], c2 = (float)c[2];  // plane centres are floats to begin with: exact
+    const float ab0 = fabsf(b0) + fabsf(b1), ab2 = fabsf(b2);
+    const bool pretest = use_pretest && P.tau <= P.max_reproj;  // (tau above the clamp makes every cell an inlier: exact path)
+    const unsigned wmagic = (unsigned)((0x100000000ull + (unsigned)P.W - 1u) / (unsigned)P.W);
+    for (int w = w0 + warp; w < w1; w += kRefWarps) {
+        const int p = w * 32 + lane;
+        int yy, xx;
+        cell_xy(p, P.W, wmagic, yy, xx);
+        const float px = (float)(xx * P.sub + P.sub / 2 - P.shiftX), py = (float)(yy * P.sub + P.sub / 2 - P.shiftY);
+        const int lc = (w - w0) * 32 + lane;
+        bool inl = false;
+        if (p < P.N) {
+            float Xf, Yf, Zf;
+            if (CACHED) { Xf = cache[lc]; Yf = cache[kCacheCells + lc]; Zf = cache[2 * kCacheCells + lc]; }
+            else { Xf = pl[p]; Yf = pl[P.N + p]; Zf = pl[2 * (size_t)P.N + p]; }
+            const float d0 = Xf - c0, d1 = Yf - c1, d2 = Zf - c2;
+            const float xq = fmaf(A0, d0, fmaf(A1, d1, fmaf(A2, d2, b0)));
+            const float yq = fmaf(A3, d0, fmaf(A4, d1, fmaf(A5, d2, b1)));
+            const float zq = fmaf(A6, d0, fmaf(A7, d1, fmaf(A8, d2, b2)));
+            const float iz = __frcp_rn(zq);
+            const float xn = xq * iz, yn = yq * iz;
+            const float un = P.f * xn, vn = P.f * yn;
+            const float du = un + (P.ppx - px), dv = vn + (P.ppy - py);
+            const float e2 = du * du + dv * dv;
+            const float ad = fabsf(d0) + fabsf(d1) + fabsf(d2);
+            // |error of du| + |error of dv| <= eps (f |1/z| (2 |d| + |b0| + |b1| + (|xn| + |yn|)(|d| + |b2|)) + |un| + |vn| + |pp - p|)
+            const float bound = 5e-7f * (P.f * fabsf(iz) * (2.f * ad + ab0 + (fabsf(xn) + fabsf(yn)) * (ad + ab2)) + fabsf(un) + fabsf(vn) +
+                                         fabsf(P.ppx - px) + fabsf(P.ppy - py));
+            const float m = 4e-3f + 2.f * bound;
+            const float lo = P.tau - m, hi = P.tau + m;
+            if (pretest && lo > 0.f && e2 < lo * lo) {
+                inl = true;
+            } else if (pretest && e2 > hi * hi) {
+                inl = false;
+            } else {
+                float err = repro_err_f(R, t0, f, cx, cy, Xf, Yf, Zf, px, py);
+                err = (P.max_reproj < err) ? P.max_reproj : err;  // std::min(err, maxReproj): NaN stays NaN
+                inl = err < P.tau;                                  // esac_util.h:406
+            }
+        }
+        const uint32_t bits = __ballot_sync(0xffffffffu, inl);
+        if (lane == 0) { mask[w] = bits; cnt[w - w0] = __popc(bits); }
+    }
+}
+
 // The same sums over the listed inlier cells only (list[i] = cell offset from the share's first cell).
 template <bool CACHED>
 __device__ __forceinline__ void lm_accumulate_list(const float* __restrict__ pl, const float* __restrict__ cache, const Problem& P,
@@ -286,6 +355,7 @@ __device__ __forceinline__ void lm_accumulate_list(const float* __restrict__ pl,
 #pragma unroll
     for (int i = 0; i < kRedN + 1; ++i) acc[i] = 0;
     const double f = (double)P.f, cx = (double)P.ppx, cy = (double)P.ppy;
+    const unsigned wmagic = (unsigned)((0x100000000ull + (unsigned)P.W - 1u) / (unsigned)P.W);
     // software pipeline: the list entry and the three coordinates of the NEXT cell are requested before the ~95 fp64
     // instructions of the current one (uncached shares read both from L2: two dependent round trips per cell otherwise,
     // which 4 warps per scheduler do not cover)
@@ -307,7 +377,8 @@ __device__ __forceinline__ void lm_accumulate_list(const float* __restrict__ pl,
             else { const int p2 = w0 * 32 + lc_n; Xn = pl[p2]; Yn = pl[P.N + p2]; Zn = pl[2 * (size_t)P.N + p2]; }
         }
         const int p = w0 * 32 + lc;
-        const int yy = p / P.W, xx = p - yy * P.W;
+        int yy, xx;
+        cell_xy(p, P.W, wmagic, yy, xx);
         const double px = (double)(xx * P.sub + P.sub / 2 - P.shiftX), py = (double)(yy * P.sub + P.sub / 2 - P.shiftY);
         const double X = (double)Xf - c[0], Y = (double)Yf - c[1], Z = (double)Zf - c[2];
         const double qx = R[0] * X + R[1] * Y + R[2] * Z;
@@ -691,10 +762,17 @@ __global__ void __launch_bounds__(kRefThreads, 1) refine_kernel(const __grid_con
         const double* R = sh.cmd + C_R;
         const double* t = sh.cmd + C_T;
         const double* t0 = sh.cmd + C_PAR + 3;
-        if (cmd == CMD_FIRST) {
-            int* cnt = compact ? sh.cnt : nullptr;
-            if (cached) lm_accumulate<true, true>(pl, cell_cache, P, R, t, cen, mtent, w0, w1, t0, acc, cnt);
-            else lm_accumulate<true, false>(pl, cell_cache, P, R, t, cen, mtent, w0, w1, t0, acc, cnt);
+        if (cmd == CMD_FIRST && compact) {
+            // select the round's inliers, list them, then the sums over the list (the first evaluation of the round)
+            if (cached) lm_select<true>(pl, cell_cache, P, R, t0, t, cen, mtent, w0, w1, sh.cnt, a.pretest != 0);
+            else lm_select<false>(pl, cell_cache, P, R, t0, t, cen, mtent, w0, w1, sh.cnt, a.pretest != 0);
+            build_inlier_list(sh, mtent, w0, w1, list);
+            if (cached) lm_accumulate_list<true>(pl, cell_cache, P, R, t, cen, list, sh.n_list, w0, acc);
+            else lm_accumulate_list<false>(pl, cell_cache, P, R, t, cen, list, sh.n_list, w0, acc);
+            if (tid == 0) acc[kRedN] = (double)sh.n_list;
+        } else if (cmd == CMD_FIRST) {
+            if (cached) lm_accumulate<true, true>(pl, cell_cache, P, R, t, cen, mtent, w0, w1, t0, acc, nullptr);
+            else lm_accumulate<true, false>(pl, cell_cache, P, R, t, cen, mtent, w0, w1, t0, acc, nullptr);
         } else if (compact) {
             if (cached) lm_accumulate_list<true>(pl, cell_cache, P, R, t, cen, list, sh.n_list, w0, acc);
             else lm_accumulate_list<false>(pl, cell_cache, P, R, t, cen, list, sh.n_list, w0, acc);
@@ -704,8 +782,6 @@ __global__ void __launch_bounds__(kRefThreads, 1) refine_kernel(const __grid_con
         }
         tick(a, sh, 1);
         block_reduce_publish<kRedN + 1>(acc, sh, a, grp, cta, seq);
-        // the round's inlier list, after this block's totals are out (the other blocks build theirs while the root decides)
-        if (cmd == CMD_FIRST && compact) build_inlier_list(sh, mtent, w0, w1, list);
         tick(a, sh, 2);
         if (!root) continue;
         // ================= root: gather, decide, step =================

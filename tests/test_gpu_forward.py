@@ -185,6 +185,41 @@ def test_refine_matches_oracle(api):
         assert rot < ROT_TOL_DEG and trans < TRANS_TOL_M, (h, rot, trans)
 
 
+@pytest.mark.parametrize("kw", [
+    dict(E=2, H=60, W=80, M=24, sub=8, seed=6),                                                 # the reference's native shape
+    dict(E=2, H=120, W=160, M=16, sub=4, seed=12, noise=0.05, outlier_frac=0.3),                # many errors close to tau
+    dict(E=2, H=48, W=64, M=16, sub=8, seed=13, outdoor=True, world_offset=700.0),              # world-scale coordinates
+    dict(E=1, H=24, W=32, M=12, sub=8, seed=14, unit_scale=7000.0, noise=0.002),                # lengths in 1/7000 m
+    dict(E=1, H=30, W=40, M=12, sub=8, seed=15, shiftX=3, shiftY=-5, noise=0.1),                # shifted grid, heavy noise
+])
+def test_refinement_float_pretest_never_changes_a_decision(api, kw):
+    """The inlier selection classifies clear cells with a float evaluation + rounding-error bound and runs getReproErrs'
+    arithmetic only where in doubt (refine.cu lm_select): switching the pretest off must give bit-identical poses, rounds and
+    inlier counts -- one differing cell would change the sums.  Start poses: ground truth perturbed, so every round moves."""
+    sc = make_scene(**kw)
+    rng = np.random.default_rng(kw["seed"])
+    import cv2
+    T = np.linalg.inv(sc.gt_pose.astype(np.float64))                     # scene (world -> camera) transform
+    poses6 = np.zeros((len(sc.assign), 6))
+    scale = float(kw.get("unit_scale", 1.0)) * (5.0 if kw.get("outdoor") else 1.0)
+    for h in range(len(sc.assign)):                                      # a small motion IN THE CAMERA FRAME on top of the truth
+        dR, _ = cv2.Rodrigues(rng.normal(0, 0.004, 3))
+        R1 = dR @ T[:3, :3]
+        t1 = dR @ T[:3, 3] + rng.normal(0, 0.02 * scale, 3)
+        poses6[h, :3] = cv2.Rodrigues(R1)[0].ravel()
+        poses6[h, 3:] = t1
+    ctx = api.context()
+    outs = []
+    for pre in (0, 1):
+        ctx.set_option("refine_pretest", pre)
+        outs.append(api.refine_poses(sc.coords, sc.assign, poses6, sc.shiftX, sc.shiftY, sc.f, sc.ppx, sc.ppy, sc.tau, sc.max_reproj, sc.sub))
+    ctx.set_option("refine_pretest", 1)
+    assert outs[0][2].tolist() == outs[1][2].tolist()          # inlier counts
+    assert outs[0][1].tolist() == outs[1][1].tolist()          # accepted rounds
+    assert np.array_equal(outs[0][0], outs[1][0])              # poses, bit for bit
+    assert outs[0][2].max() >= 4 and outs[0][1].max() >= 1     # something was refined
+
+
 def test_bad_arguments_raise(api):
     sc = make_scene(E=1, H=30, W=40, M=8, sub=8, seed=1)
     out = np.zeros((4, 4), np.float32)
