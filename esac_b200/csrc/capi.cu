@@ -78,7 +78,7 @@ struct esacb200_ctx {
     int refine_profile = 0;    // 1: block 0 of the refinement kernel records phase cycle counts (esacb200_get_refine_profile)
     int refine_jobs_per_group = 3;
     int sample_prefilter = 1;
-    int sample_span0 = 128;       // tries per hypothesis in the first wave
+    int sample_span0 = 256;       // tries per hypothesis in the first wave (a multiple of the 256-try pass of a prefilter CTA)
     float sample_window = 1.25f;  // later waves: window / acceptance rate
     int sample_waves = 7;
     float sample_tail_boost = 1.f;  // window factor once <= 64 hypotheses are left in a lane (x2 more for <= 8)
@@ -671,7 +671,7 @@ int esacb200_set_option(esacb200_ctx* ctx, const char* key, double v) {
     else if (!strcmp(key, "sample_prefilter")) ctx->sample_prefilter = v != 0;
     else if (!strcmp(key, "sample_tail_boost")) ctx->sample_tail_boost = v < 1 ? 1.f : (float)v;
     else if (!strcmp(key, "sample_trace")) ctx->sample_trace = v != 0;
-    else if (!strcmp(key, "sample_span0")) ctx->sample_span0 = v < 128 ? 128 : ((int)v + 127) / 128 * 128;
+    else if (!strcmp(key, "sample_span0")) ctx->sample_span0 = v < 256 ? 256 : ((int)v + 255) / 256 * 256;
     else if (!strcmp(key, "sample_window")) ctx->sample_window = v < 0.05 ? 0.05f : (float)v;
     else if (!strcmp(key, "sample_waves")) ctx->sample_waves = v < 0 ? 0 : (v > 64 ? 64 : (int)v);
     else if (!strcmp(key, "upload_split")) ctx->upload_split = v != 0;  // host maps in two halves, sampling under the second copy

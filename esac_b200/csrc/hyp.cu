@@ -130,40 +130,119 @@ __global__ void sample_init_kernel(const __grid_constant__ SampleArgs a) {
     }
 }
 
-// ---- wave phase 1: fp32 prefilter, one thread per try --------------------------------------------------------
-__global__ void __launch_bounds__(kTryThreads, 8) prefilter_kernel(const __grid_constant__ SampleArgs a) {
-    TraceScope trace(a.trace, a.trace_slot);
-    const int n_unres = a.st.counters[0];
-    const int span = a.st.counters[3];
-    const int cph = (span + kTryThreads - 1) / kTryThreads;  // chunks per hypothesis
-    const long long n_items = (long long)n_unres * cph;
-    const int lane = threadIdx.x & 31;
-    for (long long item = blockIdx.x; item < n_items; item += gridDim.x) {
-        const int u = (int)(item / cph), c = (int)(item - (long long)u * cph);
-        const int h = a.st.list[u];
-        const int t0 = a.st.base[h];
-        const int off = c * kTryThreads + threadIdx.x;
-        const int t = t0 + off;
-        bool pass = false;
-        if (off < span && t < a.limit) {
-            int cx[4], cy[4];
-            float obj[4][3], img[4][2];
-            load_try(a, h, t, cx, cy, obj, img);
-            pass = !a.use_prefilter || p3p_may_pass_fast(obj, img, a.P.f, a.P.ppx, a.P.ppy, a.P.tau);
+// ---- wave phase 1: fp32 prefilter, TWO tries per thread on the packed f32x2 pipe -----------------------------------
+constexpr int kPackTries = 2 * kTryThreads;  // tries per CTA pass: thread i judges tries i and i + 128 of the 256-try chunk
+// One work item of the prefilter: 256 consecutive tries of one hypothesis, two per thread.
+struct PreItem {
+    int h, ta, tb;          // hypothesis, this thread's two tries
+    bool valid0, valid1;
+    unsigned cell[8];       // (y << 16) | x of the 2 x 4 cells
+};
+__device__ __forceinline__ void cp_async16(void* smem, const void* gmem) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"((unsigned)__cvta_generic_to_shared(smem)), "l"(gmem) : "memory");
+}
+// Decodes item -> (hypothesis, tries), draws the 2 x 4 cells and starts the 8 gathers of 16 bytes straight into shared
+// memory (cp.async: no registers are held while they are in flight).
+__device__ __forceinline__ void prefilter_issue(const SampleArgs& a, long long item, int cph, int span, float4 (*dst)[kTryThreads], PreItem& it) {
+    const int u = (int)(item / cph), c = (int)(item - (long long)u * cph);
+    it.h = a.st.list[u];
+    const int t0 = a.st.base[it.h];
+    const int off0 = c * kPackTries + threadIdx.x, off1 = off0 + kTryThreads;
+    it.valid0 = off0 < span && t0 + off0 < a.limit;
+    it.valid1 = off1 < span && t0 + off1 < a.limit;
+    // an invalid half re-judges try t0 (in range for every listed hypothesis) and is masked out afterwards
+    it.ta = it.valid0 ? t0 + off0 : t0;
+    it.tb = it.valid1 ? t0 + off1 : t0;
+    if (!(it.valid0 || it.valid1)) return;
+    const Problem& P = a.P;
+    const float4* pl = a.coords4 + (size_t)a.assign32[it.h] * P.N;
+#pragma unroll
+    for (int k = 0; k < 2; ++k) {
+        const int t = k == 0 ? it.ta : it.tb;
+        int cx[4], cy[4];
+        if (a.injected) {
+            const int* cc = a.injected + ((size_t)it.h * a.inj_T + t) * 8;
+            for (int j = 0; j < 4; ++j) { cx[j] = cc[2 * j]; cy[j] = cc[2 * j + 1]; }
+        } else {
+            draw_minimal_set(a.seed, (uint32_t)(it.h * a.hyp_stride + a.hyp_offset), (uint32_t)t, P.W, P.H, cx, cy);
         }
-        // warp-aggregated append of the survivors
-        const unsigned m = __ballot_sync(0xffffffffu, pass);
-        if (m) {
-            int basei = 0;
-            if (lane == __ffs(m) - 1) basei = atomicAdd(&a.st.counters[1], __popc(m));
-            basei = __shfl_sync(0xffffffffu, basei, __ffs(m) - 1);
-            if (pass) {
-                const int idx = basei + __popc(m & ((1u << lane) - 1u));
-                if (idx < a.st.cap) a.st.surv[idx] = make_int2(h, t);
-                else atomicMin(&a.st.ovf[h], t);  // list full: this hypothesis resumes from here in the next wave
-            }
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            it.cell[k * 4 + j] = ((unsigned)cy[j] << 16) | (unsigned)cx[j];
+            cp_async16(&dst[k * 4 + j][threadIdx.x], pl + (cy[j] * P.W + cx[j]));
         }
     }
+}
+
+// ---- wave phase 1: fp32 prefilter, TWO tries per thread on the packed f32x2 pipe, gathers one item ahead ---------------
+// The math of an item (~2700 instructions per thread, branch-free) runs while the 8 random 16-byte gathers of the NEXT item
+// are in flight: with 16-20 warps per SM (the two-try pack needs ~128 registers) nothing else would cover their L2 latency
+// (ncu before: long_scoreboard 1.9 of the 6.2 stall cycles per issued instruction at 47 % issue utilisation).
+// What it did NOT buy (profiles/r02o_prefilter_*.txt): the stage's time.  One 3.67 M-try launch takes 266 us against 277 us for
+// the one-try-per-thread kernel it replaces, although a try now costs 1336 instead of 2024 issue slots: both versions hold 1024
+// tries per SM in flight (64 registers per try) and a try's dependent instruction chain is as long as before, so the issue
+// slots saved turn into idle ones (issue utilisation 70 % -> 50 %).  96 registers (5 CTAs per SM) spill and run slower.
+__global__ void __launch_bounds__(kTryThreads, 4) prefilter_kernel(const __grid_constant__ SampleArgs a) {
+    TraceScope trace(a.trace, a.trace_slot);
+    __shared__ float4 s_obj[2][8][kTryThreads];  // [buffer][try * 4 + point][thread]
+    const int n_unres = a.st.counters[0];
+    const int span = a.st.counters[3];
+    const int cph = (span + kPackTries - 1) / kPackTries;  // chunks per hypothesis
+    const long long n_items = (long long)n_unres * cph;
+    const int lane = threadIdx.x & 31, tid = threadIdx.x;
+    const Problem& P = a.P;
+    PreItem cur, nxt;
+    long long item = blockIdx.x;
+    if (item < n_items) prefilter_issue(a, item, cph, span, s_obj[0], cur);
+    asm volatile("cp.async.commit_group;" ::: "memory");
+    int buf = 0;
+    for (; item < n_items; item += gridDim.x) {
+        const long long ni = item + gridDim.x;
+        if (ni < n_items) prefilter_issue(a, ni, cph, span, s_obj[buf ^ 1], nxt);
+        asm volatile("cp.async.commit_group;" ::: "memory");
+        asm volatile("cp.async.wait_group 1;" ::: "memory");  // everything but the group just committed has landed
+        bool pass0 = false, pass1 = false;
+        if (cur.valid0 || cur.valid1) {
+            float obj0[4][3], img0[4][2], obj1[4][3], img1[4][2];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const float4 v0 = s_obj[buf][j][tid], v1 = s_obj[buf][4 + j][tid];
+                obj0[j][0] = v0.x; obj0[j][1] = v0.y; obj0[j][2] = v0.z;
+                obj1[j][0] = v1.x; obj1[j][1] = v1.y; obj1[j][2] = v1.z;
+                const unsigned c0 = cur.cell[j], c1 = cur.cell[4 + j];
+                img0[j][0] = (float)((int)(c0 & 0xffffu) * P.sub + P.sub / 2 - P.shiftX);
+                img0[j][1] = (float)((int)(c0 >> 16) * P.sub + P.sub / 2 - P.shiftY);
+                img1[j][0] = (float)((int)(c1 & 0xffffu) * P.sub + P.sub / 2 - P.shiftX);
+                img1[j][1] = (float)((int)(c1 >> 16) * P.sub + P.sub / 2 - P.shiftY);
+            }
+            if (a.use_prefilter) p3p_may_pass_fast2(obj0, img0, obj1, img1, P.f, P.ppx, P.ppy, P.tau, pass0, pass1);
+            else pass0 = pass1 = true;
+            pass0 = pass0 && cur.valid0;
+            pass1 = pass1 && cur.valid1;
+        }
+        // warp-aggregated append of the survivors (both halves in one reservation)
+        const unsigned m0 = __ballot_sync(0xffffffffu, pass0), m1 = __ballot_sync(0xffffffffu, pass1);
+        if (m0 | m1) {
+            const int n0 = __popc(m0);
+            int basei = 0;
+            if (lane == 0) basei = atomicAdd(&a.st.counters[1], n0 + __popc(m1));
+            basei = __shfl_sync(0xffffffffu, basei, 0);
+            const unsigned lt = (1u << lane) - 1u;
+            if (pass0) {
+                const int idx = basei + __popc(m0 & lt);
+                if (idx < a.st.cap) a.st.surv[idx] = make_int2(cur.h, cur.ta);
+                else atomicMin(&a.st.ovf[cur.h], cur.ta);  // list full: this hypothesis resumes from here in the next wave
+            }
+            if (pass1) {
+                const int idx = basei + n0 + __popc(m1 & lt);
+                if (idx < a.st.cap) a.st.surv[idx] = make_int2(cur.h, cur.tb);
+                else atomicMin(&a.st.ovf[cur.h], cur.tb);
+            }
+        }
+        cur = nxt;
+        buf ^= 1;
+    }
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
 }
 
 __device__ void advance_wave(const SampleState& st, int limit, float window, float tail_boost);
@@ -237,8 +316,8 @@ __device__ void advance_wave(const SampleState& st, int limit, float window, flo
         // few hypotheses left: their tries cost next to nothing, a further wave costs a full verdict latency -- ask for more
         const double boost = nn <= 8 ? tail_boost * 2. : (nn <= 64 ? tail_boost : 1.);
         double next_span = (double)window * boost * tried / hits;
-        next_span = next_span < 128. ? 128. : (next_span > 65536. ? 65536. : next_span);
-        st.counters[3] = ((int)next_span + kTryThreads - 1) / kTryThreads * kTryThreads;
+        next_span = next_span < 256. ? 256. : (next_span > 65536. ? 65536. : next_span);
+        st.counters[3] = ((int)next_span + kPackTries - 1) / kPackTries * kPackTries;
         st.counters[0] = nn;
         st.counters[1] = 0;
         st.counters[4] = 0;  // ticket of the next exact_kernel
@@ -363,7 +442,7 @@ int launch_sample(const float* coords, float4* coords4, const int* assign32, con
         }
         if (bound[g] <= 0) continue;
         sample_init_kernel<<<(bound[g] + 255) / 256, 256, 0, sg>>>(a); ++launches;
-        const int grid = sm_count * 16;
+        const int grid = sm_count * 4;  // persistent: every CTA resident (4 x 128 threads x 128 registers per SM), ~14 items each in a bulk wave
         for (int r = 0; r < n_waves; ++r) {
             a.trace_slot = (g * 32 + r) * 2;
             prefilter_kernel<<<grid, kTryThreads, 0, sg>>>(a); ++launches;

@@ -52,7 +52,7 @@ if "--native" in sys.argv:  # the reference's native shape: 60x80 cells (sub 8),
         print(f"native 60x80 M=256 : sample ms {np.mean(ms):.3f} total {np.mean(tot):.3f} launches {st['kernel_launches']}")
 
 if "--trace" in sys.argv:  # timeline of the waves: who runs when
-    for lanes, spread in ((2, 0), (4, 0)):
+    for lanes, spread in ((1, 0), (2, 0)):
         ctx.set_option("sample_tail_boost", 1.0)
         ctx.set_option("sample_groups", lanes); ctx.set_option("sample_trace", 1)
         ctx.set_option("sample_span0", 128); ctx.set_option("sample_window", 1.25); ctx.set_option("sample_waves", 7)
