@@ -1620,6 +1620,17 @@ void esacb200_host_try(const float* obj12, const float* img8, float f, float ppx
     *accept = (ok && minimal_set_gate(obj, img, p, (double)f, (double)ppx, (double)ppy, tau)) ? 1 : 0;
 }
 
+void esacb200_host_try_verdict(const float* obj12, const float* img8, float f, float ppx, float ppy, float tau, int* accept) {
+    float obj[4][3], img[4][2];
+    for (int i = 0; i < 4; ++i) {
+        for (int c = 0; c < 3; ++c) obj[i][c] = obj12[i * 3 + c];
+        for (int c = 0; c < 2; ++c) img[i][c] = img8[i * 2 + c];
+    }
+    Pose p;
+    const bool ok = p3p_pose(obj, img, (double)f, (double)ppx, (double)ppy, p, 1.25 * (double)tau + 1.);  // as hyp.cu exact_try(verdict_only)
+    *accept = (ok && minimal_set_gate(obj, img, p, (double)f, (double)ppx, (double)ppy, tau)) ? 1 : 0;
+}
+
 void esacb200_host_project(const double pose6[6], float f, float ppx, float ppy, const float X[3], float uv_f[2],
                            double uv[2], double J12[12]) {
     double R[9], dRdr[27];

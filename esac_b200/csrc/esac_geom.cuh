@@ -652,12 +652,56 @@ ESAC_HD int p3p_lambdas(const T y[3][3], const T x[3][3], T lam[4][3], T& amax, 
     return ns;
 }
 
+// A 4th correspondence for the early exit of p3p_solve: scene point, pixel, camera, squared pixel distance beyond which a
+// candidate is hopeless.
+struct FourthPoint {
+    double X[3], u, v, f, ppx, ppy, reject2;
+};
+
 // All P3P solutions (R row-major, t), polished to machine precision.  Returns the count (0..4).
-ESAC_HDN int p3p_solve(const double y[3][3], const double x[3][3], double Rs[4][9], double ts[4][3]) {
+// With `fourth` (the sampling stage's verdicts): when EVERY candidate depth triple, still unpolished, puts the 4th point
+// further than sqrt(reject2) pixels from where it was seen, no solution can pass the 4-point gate and the polish / alignment
+// of up to four candidates (most of this function) is skipped: returns -1.  The 4th point is carried over in the frame of
+// the scene triangle (x4 - x0 = al u1 + be u2 + ga u1 x u2, coefficients preserved by a rigid motion), so no rotation is
+// needed; a candidate whose distance equations are not met to 1e-6 is not trusted and disables the exit.
+ESAC_HDN int p3p_solve(const double y[3][3], const double x[3][3], double Rs[4][9], double ts[4][3], const FourthPoint* fourth = nullptr) {
     double lams[4][3], amax, cs[3], ss[3];
     bool unc;
     int nl = p3p_lambdas<double>(y, x, lams, amax, cs, ss, unc);
     const double c12 = cs[0], c13 = cs[1], c23 = cs[2], s12 = ss[0], s13 = ss[1], s23 = ss[2];
+    if (fourth && nl > 0) {
+        double u1[3], u2[3], d4[3], nw[3];
+        for (int c = 0; c < 3; ++c) { u1[c] = x[1][c] - x[0][c]; u2[c] = x[2][c] - x[0][c]; d4[c] = fourth->X[c] - x[0][c]; }
+        cross3(u1, u2, nw);
+        const double g11 = u1[0] * u1[0] + u1[1] * u1[1] + u1[2] * u1[2], g22 = u2[0] * u2[0] + u2[1] * u2[1] + u2[2] * u2[2];
+        const double g12 = u1[0] * u2[0] + u1[1] * u2[1] + u1[2] * u2[2];
+        const double nn = nw[0] * nw[0] + nw[1] * nw[1] + nw[2] * nw[2], det = g11 * g22 - g12 * g12;
+        if (det > 1e-12 * g11 * g22 && nn > 0) {
+            const double v1 = d4[0] * u1[0] + d4[1] * u1[1] + d4[2] * u1[2], v2 = d4[0] * u2[0] + d4[1] * u2[1] + d4[2] * u2[2];
+            const double idet = 1. / det;
+            const double al = (v1 * g22 - v2 * g12) * idet, be = (v2 * g11 - v1 * g12) * idet;
+            const double ga = (d4[0] * nw[0] + d4[1] * nw[1] + d4[2] * nw[2]) / nn;
+            const double sa = sqrt(amax);
+            bool hopeless = true;
+            for (int d = 0; d < nl && hopeless; ++d) {
+                const double l0 = lams[d][0], l1 = lams[d][1], l2 = lams[d][2];
+                const double res = fabs(l0 * l0 + l1 * l1 - 2 * c12 * l0 * l1 - s12) + fabs(l0 * l0 + l2 * l2 - 2 * c13 * l0 * l2 - s13) +
+                                   fabs(l1 * l1 + l2 * l2 - 2 * c23 * l1 * l2 - s23);
+                if (!(res < 1e-6)) { hopeless = false; break; }
+                double P0[3], a1[3], a2[3], m[3];
+                for (int c = 0; c < 3; ++c) { P0[c] = l0 * sa * y[0][c]; a1[c] = l1 * sa * y[1][c] - P0[c]; a2[c] = l2 * sa * y[2][c] - P0[c]; }
+                cross3(a1, a2, m);
+                const double xc = P0[0] + al * a1[0] + be * a2[0] + ga * m[0];
+                const double yc = P0[1] + al * a1[1] + be * a2[1] + ga * m[1];
+                const double zc = P0[2] + al * a1[2] + be * a2[2] + ga * m[2];
+                const double iz = 1. / zc;
+                const double du = fourth->ppx + fourth->f * xc * iz - fourth->u, dv = fourth->ppy + fourth->f * yc * iz - fourth->v;
+                const double e = du * du + dv * dv;
+                if (!(e > fourth->reject2)) hopeless = false;  // close enough, or NaN: the full path decides
+            }
+            if (hopeless) return -1;
+        }
+    }
     double Fw[9];
     if (nl > 0 && !tri_frame<double>(x[0], x[1], x[2], Fw)) return 0;
     int ns = 0;
@@ -709,15 +753,22 @@ ESAC_HD void bearing(float u, float v, double f, double ppx, double ppy, double 
 // solution with the smallest squared reprojection error of the 4th (Appendix A of SURVEY.md: the
 // 4th point only disambiguates).  img = integer pixel positions as float, obj = float scene points.
 // Returns false when no solution exists (the reference retries, esac_util.h:189-200).
-ESAC_HD bool p3p_pose(const float obj[4][3], const float img[4][2], double f, double ppx, double ppy, Pose& pose) {
+// reject_px > 0 (sampling verdicts only): give up -- return false -- as soon as no candidate brings the 4th point within
+// reject_px pixels (p3p_solve's early exit); the caller must then not use `pose`.
+ESAC_HD bool p3p_pose(const float obj[4][3], const float img[4][2], double f, double ppx, double ppy, Pose& pose, double reject_px = 0.) {
     double y[3][3], x[3][3];
     for (int i = 0; i < 3; ++i) {
         bearing(img[i][0], img[i][1], f, ppx, ppy, y[i]);
         for (int c = 0; c < 3; ++c) x[i][c] = (double)obj[i][c];
     }
     double Rs[4][9], ts[4][3];
-    int n = p3p_solve(y, x, Rs, ts);
-    if (n == 0) return false;
+    FourthPoint fp;
+    if (reject_px > 0.) {
+        fp.X[0] = obj[3][0]; fp.X[1] = obj[3][1]; fp.X[2] = obj[3][2];
+        fp.u = img[3][0]; fp.v = img[3][1]; fp.f = f; fp.ppx = ppx; fp.ppy = ppy; fp.reject2 = reject_px * reject_px;
+    }
+    int n = p3p_solve(y, x, Rs, ts, reject_px > 0. ? &fp : nullptr);
+    if (n <= 0) return false;
     int best = 0;
     double beste = 0;
     for (int s = 0; s < n; ++s) {

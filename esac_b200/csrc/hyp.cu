@@ -96,11 +96,16 @@ __device__ __forceinline__ void load_try(const SampleArgs& a, int h, int t, int 
     }
 }
 
-__device__ __noinline__ bool exact_try(const SampleArgs& a, int h, int t, Pose& pose, int cx[4], int cy[4], bool& solved) {
+// verdict_only: the caller wants accept / reject and nothing else, so a try none of whose P3P candidates brings the 4th
+// point within 1.25 tau + 1 px (measured on the unpolished depths) is rejected before polish / alignment / Rodrigues / gate --
+// that is ~60 % of what survives the float prefilter's 2 tau band.  `solved` and `pose` are then meaningless; emit_kernel,
+// which needs the failure state of an exhausted hypothesis' last try, calls with verdict_only = false.
+__device__ __noinline__ bool exact_try(const SampleArgs& a, int h, int t, Pose& pose, int cx[4], int cy[4], bool& solved,
+                                       bool verdict_only = false) {
     float obj[4][3], img[4][2];
     load_try(a, h, t, cx, cy, obj, img);
     const double f = (double)a.P.f, ppx = (double)a.P.ppx, ppy = (double)a.P.ppy;
-    solved = p3p_pose(obj, img, f, ppx, ppy, pose);
+    solved = p3p_pose(obj, img, f, ppx, ppy, pose, verdict_only ? 1.25 * (double)a.P.tau + 1. : 0.);
     return solved && minimal_set_gate(obj, img, pose, f, ppx, ppy, a.P.tau);
 }
 
@@ -257,7 +262,7 @@ __global__ void __launch_bounds__(128) exact_kernel(const __grid_constant__ Samp
         Pose pose;
         int cx[4], cy[4];
         bool solved;
-        if (exact_try(a, ht.x, ht.y, pose, cx, cy, solved)) {
+        if (exact_try(a, ht.x, ht.y, pose, cx, cy, solved, true)) {
             // stage the accepted pose so that emit_kernel does not have to solve it again
             unsigned slot = (unsigned)atomicAdd(&a.st.counters[2], 1);
             if (slot < (unsigned)a.st.cap_acc) {
@@ -355,7 +360,7 @@ __global__ void __launch_bounds__(kTryThreads) tail_kernel(const __grid_constant
                 Pose pose;
                 int cx[4], cy[4];
                 bool solved;
-                if (exact_try(a, h, s_list[i], pose, cx, cy, solved)) atomicMin(&s_best, s_list[i]);
+                if (exact_try(a, h, s_list[i], pose, cx, cy, solved, true)) atomicMin(&s_best, s_list[i]);
             }
             __syncthreads();
             if (s_best != kNoTry) break;
@@ -442,7 +447,9 @@ int launch_sample(const float* coords, float4* coords4, const int* assign32, con
         }
         if (bound[g] <= 0) continue;
         sample_init_kernel<<<(bound[g] + 255) / 256, 256, 0, sg>>>(a); ++launches;
-        const int grid = sm_count * 4;  // persistent: every CTA resident (4 x 128 threads x 128 registers per SM), ~14 items each in a bulk wave
+        // persistent: every CTA resident (4 x 128 threads x 128 registers fill an SM's register file), ~14 items each in a bulk wave;
+        // 3 CTAs per SM + 64-thread verdict CTAs in the room that leaves was measured slower (profiles/r02o_sample_room_for_verdicts.txt)
+        const int grid = sm_count * 4;
         for (int r = 0; r < n_waves; ++r) {
             a.trace_slot = (g * 32 + r) * 2;
             prefilter_kernel<<<grid, kTryThreads, 0, sg>>>(a); ++launches;

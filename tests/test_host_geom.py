@@ -211,7 +211,7 @@ def test_float_prefilter_never_rejects_an_accepted_try(lib, kw, which):
     e = sc.gt_expert if which == "gt" else 1 - sc.gt_expert
     rng = np.random.default_rng(5)
     pl = sc.coords[e]
-    mp, ac = C.c_int(), C.c_int()
+    mp, ac, ev = C.c_int(), C.c_int(), C.c_int()
     n_acc = n_may = 0
     n = 20000
     for _ in range(n):
@@ -223,6 +223,8 @@ def test_float_prefilter_never_rejects_an_accepted_try(lib, kw, which):
         img = np.ascontiguousarray(np.stack([xs * 8 + 4, ys * 8 + 4], 1).astype(np.float32))
         lib.esacb200_host_try(_ptr(obj), _ptr(img), sc.f, sc.ppx, sc.ppy, sc.tau, 2.0, C.byref(mp), C.byref(ac))  # 2.0 = kPrefilterMargin, the shipping band
         assert not (ac.value and not mp.value)
+        lib.esacb200_host_try_verdict(_ptr(obj), _ptr(img), sc.f, sc.ppx, sc.ppy, sc.tau, C.byref(ev))
+        assert ev.value == ac.value   # the early exit of the verdict path never changes the exact decision
         n_acc += ac.value; n_may += mp.value
     if which == "gt":
         assert n_acc > 500           # the invariant was exercised on accepted tries
