@@ -50,7 +50,9 @@ enum { CMD_EVAL = 1, CMD_FIRST = 2, CMD_EXIT = 3 };
 enum { C_PAR = 0, C_R = 6, C_T = 15, C_CMD = 18, C_JOB = 19, C_SEL = 20, C_COUNT = 21 };
 
 struct RefShared {
-    double red[kRefWarps][32];
+    double red[kRefWarps][32];   // per-warp partial sums of the block reduction
+    double gat[kRefWarps][32];   // ... of the root's gather (its own buffer: the root's warps may enter the gather while warp 0
+                                 // still sums `red` for the block's own totals -- found by compute-sanitizer racecheck)
     double tot[32];
     double cmd[kSlot];
     // ---- root only ----
@@ -168,14 +170,14 @@ __device__ __forceinline__ void root_gather(RefShared& sh, const RefineArgs& a, 
                 for (int k = 0; k < 10; ++k) s += x[k];
             }
         }
-        sh.red[warp][lane] = s;
+        sh.gat[warp][lane] = s;
     }
     tick(a, sh, 3);
     __syncthreads();
     if (tid < NV) {
         double s = 0;
 #pragma unroll
-        for (int w = 0; w < kRefWarps; ++w) s += sh.red[w][tid];
+        for (int w = 0; w < kRefWarps; ++w) s += sh.gat[w][tid];
         sh.tot[tid] = s;
     }
     __syncthreads();
@@ -669,7 +671,8 @@ __global__ void __launch_bounds__(kRefThreads, 1) refine_kernel(const __grid_con
         // ================= root, warp 0: produce the next command =================
         if (root && warp == 0) {
             if (lane == 0) {
-                while (sh.finished) {  // draw jobs until one needs work or the list ends
+                bool need_job = sh.finished != 0;
+                while (need_job) {  // draw jobs until one needs work or the list ends
                     const int job = dynamic ? atomicAdd(a.job_counter, 1) : (sh.job < 0 ? grp : n_jobs);
                     sh.job = job;
                     if (job >= n_jobs) break;
@@ -688,6 +691,7 @@ __global__ void __launch_bounds__(kRefThreads, 1) refine_kernel(const __grid_con
                     sh.rounds = 0; sh.sel = 0; sh.step = 0;
                     sh.mode = CMD_FIRST;
                     sh.finished = 0;
+                    need_job = false;
                 }
             }
             __syncwarp();

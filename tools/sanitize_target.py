@@ -16,6 +16,13 @@ coords = torch.from_numpy(sc.coords).cuda()
 assign = torch.from_numpy(sc.assign).cuda()
 out = torch.zeros(4, 4, device="cuda")
 print("forward", api.forward(coords, assign, out, *sc.params), ctx.stats()["kernel_launches"])
+# multi-CTA refinement groups (LL exchange, shared-memory inlier lists) and an uncached share (global inlier list)
+big = make_scene(E=1, H=120, W=160, M=16, sub=4, seed=5)
+cb, ab = torch.from_numpy(big.coords).cuda(), torch.from_numpy(big.assign).cuda()
+for grp in (0, 2):
+    ctx.set_option("refine_group", grp)
+    print("forward 120x160 group", grp, api.forward(cb, ab, out, *big.params), ctx.stats()["refine_group"])
+ctx.set_option("refine_group", 0)
 sc = make_scene(E=2, H=24, W=32, M=48, sub=8, seed=3)
 coords = torch.from_numpy(sc.coords).cuda()
 grads = torch.zeros_like(coords)
