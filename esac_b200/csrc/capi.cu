@@ -80,7 +80,7 @@ struct esacb200_ctx {
     int sample_prefilter = 1;
     int sample_span0 = 256;       // tries per hypothesis in the first wave (a multiple of the 256-try pass of a prefilter CTA)
     float sample_window = 1.25f;  // later waves: window / acceptance rate
-    int sample_waves = 7;
+    int sample_waves = 6;         // launched unconditionally (empty ones cost ~6 us each); what is left after them goes to tail_kernel
     float sample_tail_boost = 1.f;  // window factor once <= 64 hypotheses are left in a lane (x2 more for <= 8)
     int sample_trace = 0;         // 1: prefilter / exact kernels stamp first-CTA-start / last-CTA-end times (esacb200_get_sample_trace)
     int smp_groups_last = 0;      // lanes of the last run_sample (diagnostics read-back)
