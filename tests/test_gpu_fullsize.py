@@ -113,3 +113,32 @@ def test_split_upload_of_host_maps_changes_nothing(api, kw):
         assert np.array_equal(res["split"][1], res[mode][1])
         assert np.array_equal(res["split"][3], res[mode][3]) and np.array_equal(res["split"][4], res[mode][4])
         assert np.array_equal(res["split"][2], res[mode][2])
+
+
+def test_refinement_code_paths_agree_at_full_resolution(api):
+    """The refinement kernel has three ways to walk a CTA's share of the map: cells + inlier list in shared memory (share <= 96
+    words: the forward's 148-CTA group), inlier list in global scratch (<= 2048 words), and predicated passes over all cells
+    (larger shares).  Forcing the group size selects each of them at 480x640; rounds and inlier counts must be identical and the
+    poses equal up to the summation order (1e-9)."""
+    sc = make_scene(E=1, H=480, W=640, M=6, sub=1, seed=21, outlier_frac=0.4)
+    import cv2
+    rng = np.random.default_rng(21)
+    T = np.linalg.inv(sc.gt_pose.astype(np.float64))
+    poses6 = np.zeros((len(sc.assign), 6))
+    for h in range(len(sc.assign)):
+        dR, _ = cv2.Rodrigues(rng.normal(0, 0.003, 3))
+        poses6[h, :3] = cv2.Rodrigues(dR @ T[:3, :3])[0].ravel()
+        poses6[h, 3:] = dR @ T[:3, 3] + rng.normal(0, 0.01, 3)
+    ctx = api.context()
+    outs = {}
+    try:
+        for grp in (148, 16, 2):   # 148: 65 words per CTA (shared-memory lists); 16: 600 words (global lists); 2: 4800 words (no lists)
+            ctx.set_option("refine_group", grp)
+            outs[grp] = api.refine_poses(sc.coords, sc.assign, poses6, sc.shiftX, sc.shiftY, sc.f, sc.ppx, sc.ppy, sc.tau, sc.max_reproj, sc.sub)
+    finally:
+        ctx.set_option("refine_group", 0)
+    assert outs[148][1].max() >= 1 and outs[148][2].min() > 1000
+    for grp in (16, 2):
+        assert outs[grp][1].tolist() == outs[148][1].tolist()
+        assert outs[grp][2].tolist() == outs[148][2].tolist()
+        assert np.abs(outs[grp][0] - outs[148][0]).max() < 1e-9
