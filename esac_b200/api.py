@@ -112,7 +112,7 @@ def load_library() -> C.CDLL:
     lib.esacb200_host_p3p_pose.restype = i32
     lib.esacb200_host_try.argtypes = [vp, vp, f32, f32, f32, f32, f32, C.POINTER(i32), C.POINTER(i32)]
     lib.esacb200_host_try.restype = None
-    lib.esacb200_host_try_verdict.argtypes = [vp, vp, f32, f32, f32, f32, C.POINTER(i32)]
+    lib.esacb200_host_try_verdict.argtypes = [vp, vp, f32, f32, f32, f32, C.POINTER(i32), vp]
     lib.esacb200_host_try_verdict.restype = None
     lib.esacb200_host_project.argtypes = [vp, f32, f32, f32, vp, vp, vp, vp]
     lib.esacb200_host_project.restype = None

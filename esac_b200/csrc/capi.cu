@@ -1620,7 +1620,8 @@ void esacb200_host_try(const float* obj12, const float* img8, float f, float ppx
     *accept = (ok && minimal_set_gate(obj, img, p, (double)f, (double)ppx, (double)ppy, tau)) ? 1 : 0;
 }
 
-void esacb200_host_try_verdict(const float* obj12, const float* img8, float f, float ppx, float ppy, float tau, int* accept) {
+void esacb200_host_try_verdict(const float* obj12, const float* img8, float f, float ppx, float ppy, float tau, int* accept,
+                               double* pose6) {
     float obj[4][3], img[4][2];
     for (int i = 0; i < 4; ++i) {
         for (int c = 0; c < 3; ++c) obj[i][c] = obj12[i * 3 + c];
@@ -1629,6 +1630,8 @@ void esacb200_host_try_verdict(const float* obj12, const float* img8, float f, f
     Pose p;
     const bool ok = p3p_pose(obj, img, (double)f, (double)ppx, (double)ppy, p, 1.25 * (double)tau + 1.);  // as hyp.cu exact_try(verdict_only)
     *accept = (ok && minimal_set_gate(obj, img, p, (double)f, (double)ppx, (double)ppy, tau)) ? 1 : 0;
+    if (pose6 && ok)
+        for (int i = 0; i < 3; ++i) { pose6[i] = p.r[i]; pose6[3 + i] = p.t[i]; }
 }
 
 void esacb200_host_project(const double pose6[6], float f, float ppx, float ppy, const float X[3], float uv_f[2],

@@ -669,6 +669,7 @@ ESAC_HDN int p3p_solve(const double y[3][3], const double x[3][3], double Rs[4][
     bool unc;
     int nl = p3p_lambdas<double>(y, x, lams, amax, cs, ss, unc);
     const double c12 = cs[0], c13 = cs[1], c23 = cs[2], s12 = ss[0], s13 = ss[1], s23 = ss[2];
+    int only = -1;  // >= 0: the one candidate worth polishing (verdict path)
     if (fourth && nl > 0) {
         double u1[3], u2[3], d4[3], nw[3];
         for (int c = 0; c < 3; ++c) { u1[c] = x[1][c] - x[0][c]; u2[c] = x[2][c] - x[0][c]; d4[c] = fourth->X[c] - x[0][c]; }
@@ -682,12 +683,14 @@ ESAC_HDN int p3p_solve(const double y[3][3], const double x[3][3], double Rs[4][
             const double al = (v1 * g22 - v2 * g12) * idet, be = (v2 * g11 - v1 * g12) * idet;
             const double ga = (d4[0] * nw[0] + d4[1] * nw[1] + d4[2] * nw[2]) / nn;
             const double sa = sqrt(amax);
-            bool hopeless = true;
-            for (int d = 0; d < nl && hopeless; ++d) {
+            bool hopeless = true, trusted = true;
+            double e_best = 1e300, e_second = 1e300;
+            int d_best = -1;
+            for (int d = 0; d < nl; ++d) {
                 const double l0 = lams[d][0], l1 = lams[d][1], l2 = lams[d][2];
                 const double res = fabs(l0 * l0 + l1 * l1 - 2 * c12 * l0 * l1 - s12) + fabs(l0 * l0 + l2 * l2 - 2 * c13 * l0 * l2 - s13) +
                                    fabs(l1 * l1 + l2 * l2 - 2 * c23 * l1 * l2 - s23);
-                if (!(res < 1e-6)) { hopeless = false; break; }
+                if (!(res < 1e-6)) { trusted = false; break; }
                 double P0[3], a1[3], a2[3], m[3];
                 for (int c = 0; c < 3; ++c) { P0[c] = l0 * sa * y[0][c]; a1[c] = l1 * sa * y[1][c] - P0[c]; a2[c] = l2 * sa * y[2][c] - P0[c]; }
                 cross3(a1, a2, m);
@@ -697,15 +700,24 @@ ESAC_HDN int p3p_solve(const double y[3][3], const double x[3][3], double Rs[4][
                 const double iz = 1. / zc;
                 const double du = fourth->ppx + fourth->f * xc * iz - fourth->u, dv = fourth->ppy + fourth->f * yc * iz - fourth->v;
                 const double e = du * du + dv * dv;
-                if (!(e > fourth->reject2)) hopeless = false;  // close enough, or NaN: the full path decides
+                if (!(e == e)) { trusted = false; break; }     // NaN: the full path decides
+                if (!(e > fourth->reject2)) hopeless = false;  // close enough
+                if (e < e_best) { e_second = e_best; e_best = e; d_best = d; }
+                else if (e < e_second) e_second = e;
             }
-            if (hopeless) return -1;
+            if (trusted && hopeless) return -1;
+            // One candidate far ahead of the others (twice as close to the seen pixel, and by more than a pixel): it is the one
+            // solvePnP's "smallest 4th-point error" rule will pick, so only it is polished and aligned.  Ties, untrusted
+            // candidates, or a favourite that then fails its own validity checks fall back to the full loop below.
+            if (trusted && d_best >= 0 && e_second > 4. * e_best + 1.) only = d_best;
         }
     }
     double Fw[9];
     if (nl > 0 && !tri_frame<double>(x[0], x[1], x[2], Fw)) return 0;
     int ns = 0;
-    for (int d = 0; d < nl && ns < 4; ++d) {
+    const double sa = sqrt(amax);
+    // candidate d -> polished depths -> pose in slot ns; false when it is not a valid new solution
+    auto add = [&](int d) -> bool {
         double lam[3] = {lams[d][0], lams[d][1], lams[d][2]};
         // Gauss-Newton polish on the three (normalised) distance equations
         double res = 0;
@@ -722,21 +734,23 @@ ESAC_HDN int p3p_solve(const double y[3][3], const double x[3][3], double Rs[4][
             if (!solve3(Jm, r, dl)) break;  // singular: keep the current estimate
             lam[0] -= dl[0]; lam[1] -= dl[1]; lam[2] -= dl[2];
         }
-        if (!(res < 1e-9) || !(lam[0] > 0 && lam[1] > 0 && lam[2] > 0)) continue;
-        double sa = sqrt(amax);
+        if (!(res < 1e-9) || !(lam[0] > 0 && lam[1] > 0 && lam[2] > 0)) return false;
         double P[3][3];
         for (int i = 0; i < 3; ++i)
             for (int c = 0; c < 3; ++c) P[i][c] = lam[i] * sa * y[i][c];
-        if (!align_triangles<double>(P, x, Fw, Rs[ns], ts[ns])) continue;
-        bool dup = false;  // reject duplicates (double roots)
-        for (int q = 0; q < ns; ++q) {
+        if (!align_triangles<double>(P, x, Fw, Rs[ns], ts[ns])) return false;
+        for (int q = 0; q < ns; ++q) {  // reject duplicates (double roots)
             double dd = 0;
             for (int c = 0; c < 3; ++c) dd += fabs(ts[q][c] - ts[ns][c]);
             for (int c = 0; c < 9; ++c) dd += fabs(Rs[q][c] - Rs[ns][c]);
-            if (dd < 1e-9) dup = true;
+            if (dd < 1e-9) return false;
         }
-        if (!dup) ++ns;
-    }
+        ++ns;
+        return true;
+    };
+    if (only >= 0 && add(only)) return 1;  // (a favourite that fails its own checks: every candidate, as usual)
+    ns = 0;
+    for (int d = 0; d < nl && ns < 4; ++d) add(d);
     return ns;
 }
 

@@ -27,9 +27,11 @@ int esacb200_host_p3p_pose(const float* obj12, const float* img8, float f, float
 void esacb200_host_try(const float* obj12, const float* img8, float f, float ppx, float ppy, float tau, float margin,
                        int* may_pass, int* accept);
 /* The sampling kernels' verdict path: the same exact decision, but a try none of whose P3P candidates brings the 4th point
- * within 1.25 tau + 1 px is rejected before polish / alignment (p3p_solve's early exit).  Invariant: *accept equals
- * esacb200_host_try's. */
-void esacb200_host_try_verdict(const float* obj12, const float* img8, float f, float ppx, float ppy, float tau, int* accept);
+ * within 1.25 tau + 1 px is rejected before polish / alignment (p3p_solve's early exit).  Only the candidate that is far ahead
+ * on the 4th point is polished (p3p_solve's favourite).  Invariants: *accept equals esacb200_host_try's, and for an accepted
+ * try pose6 (may be NULL) equals esacb200_host_p3p_pose's. */
+void esacb200_host_try_verdict(const float* obj12, const float* img8, float f, float ppx, float ppy, float tau, int* accept,
+                               double* pose6);
 /* cv::projectPoints for one point: float-rounded pixel + fp64 pixel + 2x6 Jacobian (rvec | tvec columns). */
 void esacb200_host_project(const double pose6[6], float f, float ppx, float ppy, const float X[3], float uv_f[2],
                            double uv[2], double J12[12]);

@@ -223,8 +223,13 @@ def test_float_prefilter_never_rejects_an_accepted_try(lib, kw, which):
         img = np.ascontiguousarray(np.stack([xs * 8 + 4, ys * 8 + 4], 1).astype(np.float32))
         lib.esacb200_host_try(_ptr(obj), _ptr(img), sc.f, sc.ppx, sc.ppy, sc.tau, 2.0, C.byref(mp), C.byref(ac))  # 2.0 = kPrefilterMargin, the shipping band
         assert not (ac.value and not mp.value)
-        lib.esacb200_host_try_verdict(_ptr(obj), _ptr(img), sc.f, sc.ppx, sc.ppy, sc.tau, C.byref(ev))
-        assert ev.value == ac.value   # the early exit of the verdict path never changes the exact decision
+        pv = np.zeros(6)
+        lib.esacb200_host_try_verdict(_ptr(obj), _ptr(img), sc.f, sc.ppx, sc.ppy, sc.tau, C.byref(ev), _ptr(pv))
+        assert ev.value == ac.value   # the early exit / favourite candidate of the verdict path never change the exact decision
+        if ac.value:                  # ... nor the pose that gets staged for an accepted try
+            pf = np.zeros(6); gate = C.c_int()
+            lib.esacb200_host_p3p_pose(_ptr(obj), _ptr(img), sc.f, sc.ppx, sc.ppy, sc.tau, _ptr(pf), C.byref(gate))
+            assert np.array_equal(pv, pf)
         n_acc += ac.value; n_may += mp.value
     if which == "gt":
         assert n_acc > 500           # the invariant was exercised on accepted tries
