@@ -6,13 +6,16 @@
 // try the sequential loop would have stopped at.  Wrong experts need ~1/P(4th point lands within tau) ~ 1e3 tries
 // per hypothesis, which makes this the most expensive stage of a step; it runs as waves of small kernels:
 //
-//   wave r (try window [base_h, base_h + span_r) of every unresolved hypothesis; span_0 = 128, then chosen on the
+//   wave r (try window [base_h, base_h + span_r) of every unresolved hypothesis; span_0 = 256, then chosen on the
 //   device from the acceptance rate seen so far, ~1.25 / p, so that ~70% of the remaining hypotheses resolve per
 //   wave and < 2x the necessary tries are evaluated):
-//     prefilter_kernel   one thread per try, fp32 only: p3p_may_pass() discards tries whose every P3P root misses
-//                        the 4th point by > 2 tau (>96% on wrong experts); survivors are appended to a global list
+//     prefilter_kernel   two tries per thread on the packed f32x2 pipe, fp32 only, branch-free: discards tries whose
+//                        every P3P root misses the 4th point by > 2 tau (>96% on wrong experts); the gathers of a
+//                        CTA's next 256-try item are in flight under the math of the current one; survivors are
+//                        appended to a global list
 //     exact_kernel       one thread per survivor: the fp64 path (p3p_pose + minimal_set_gate) whose verdict is the
-//                        only one that counts; atomicMin keeps the lowest accepted try per hypothesis
+//                        only one that counts (it leaves early when no P3P candidate can pass, and polishes only the
+//                        candidate far ahead on the 4th point); atomicMin keeps the lowest accepted try per hypothesis
 //     (advance)          the last CTA of exact_kernel marks resolved hypotheses, advances the window of the others and
 //                        rebuilds the work list
 //   tail_kernel          CTA per still-unresolved hypothesis: same two phases inside one CTA up to max_tries
@@ -21,8 +24,6 @@
 //
 // Keeping the float and double paths in different kernels matters: fused, the kernel ran at 10% issue utilisation,
 // stalled on instruction fetch (profiles/r01b_sample_kernel_ncu.json).
-#include <string.h>
-
 #include "esac_internal.h"
 #include "esac_p3p_fast.cuh"
 #include "esac_rng.cuh"
